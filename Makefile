@@ -1,0 +1,40 @@
+# Builds the in-tree shared libraries (sm_100a only; nvcc cross-compiles without a GPU).
+#   laghos_b200/lib/liblaghos_b200.so   C ABI (include/laghos_b200.h) + C++ shim (lagb_laghos_run)
+#   oracle/_build/liboracle.so          CPU oracle (test infrastructure)
+NVCC ?= nvcc
+CXX ?= g++
+ARCH = -gencode arch=compute_100a,code=sm_100a
+NVFLAGS = $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -diag-suppress 128
+CXXFLAGS = -O2 -std=c++17 -fPIC -Wall
+CS = laghos_b200/csrc
+OBJ = build/capi.o build/kernels_generic.o build/kernels_tuned.o build/problem_capi.o build/laghos_shim.o
+DEV_HDRS = $(wildcard $(CS)/device/*.cuh) $(CS)/ctx.hpp include/laghos_b200.h
+HOST_HDRS = $(wildcard $(CS)/host/*.hpp) include/laghos_b200.h
+
+all: laghos_b200/lib/liblaghos_b200.so oracle/_build/liboracle.so
+
+build/%.o: $(CS)/%.cu $(DEV_HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+build/problem_capi.o: $(CS)/problem_capi.cpp $(HOST_HDRS)
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+build/laghos_shim.o: laghos_b200/shim/laghos_shim.cpp laghos_b200/shim/laghos_shim.hpp $(HOST_HDRS)
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+laghos_b200/lib/liblaghos_b200.so: $(OBJ)
+	@mkdir -p laghos_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -ldl
+build/laghos: laghos_b200/shim/laghos_main.cpp laghos_b200/lib/liblaghos_b200.so
+	$(CXX) $(CXXFLAGS) -o $@ $< -Llaghos_b200/lib -llaghos_b200 -Wl,-rpath,'$$ORIGIN/../laghos_b200/lib'
+
+oracle/_build/liboracle.so: oracle/oracle_capi.cpp oracle/laghos_oracle.hpp oracle/smallmat.hpp $(HOST_HDRS)
+	@mkdir -p oracle/_build
+	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -o $@ oracle/oracle_capi.cpp -lpthread
+oracle/_build/oracle_cli: oracle/oracle_main.cpp oracle/laghos_oracle.hpp oracle/smallmat.hpp $(HOST_HDRS)
+	@mkdir -p oracle/_build
+	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -o $@ oracle/oracle_main.cpp -lpthread
+
+clean:
+	rm -rf build laghos_b200/lib oracle/_build
+.PHONY: all clean

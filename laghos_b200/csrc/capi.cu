@@ -1,0 +1,708 @@
+// C ABI implementation (include/laghos_b200.h): context, operator entry points,
+// device-resident PCG driver, timers, NCCL plumbing.
+#include "ctx.hpp"
+#include <algorithm>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <mutex>
+
+namespace lagb {
+
+static thread_local std::string g_err;
+int64_t g_launch_count = 0;
+void set_error(const std::string &msg) { g_err = msg; }
+
+int vec_grid(int64_t n)
+{
+   const int64_t b = (n + pcg::RB - 1)/pcg::RB;
+   return (int)std::max<int64_t>(1, std::min<int64_t>(b, 148*16));
+}
+
+// ---- timers: CUDA events on the context stream, resolved lazily ----
+static cudaEvent_t timer_event(Ctx &c)
+{
+   if (!c.timer.pool.empty()) { cudaEvent_t e = c.timer.pool.back(); c.timer.pool.pop_back(); return e; }
+   cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+static int timer_resolve(Ctx &c)
+{
+   for (int w = 0; w < 4; w++)
+   {
+      for (auto &p : c.timer.pending[w])
+      {
+         LAGB_CUDA(cudaEventSynchronize(p.second));
+         float ms = 0.f; LAGB_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+         c.timer.acc[w] += 1e-3*ms;
+         c.timer.pool.push_back(p.first); c.timer.pool.push_back(p.second);
+      }
+      c.timer.pending[w].clear();
+   }
+   return LAGB_OK;
+}
+int timer_begin(Ctx &c, int w)
+{
+   cudaEvent_t a = timer_event(c), b = timer_event(c);
+   LAGB_CUDA(cudaEventRecord(a, c.stream));
+   c.timer.pending[w].push_back({a, b});
+   return LAGB_OK;
+}
+int timer_end(Ctx &c, int w)
+{
+   LAGB_CUDA(cudaEventRecord(c.timer.pending[w].back().second, c.stream));
+   if (c.timer.pending[w].size() > 4096) { return timer_resolve(c); }
+   return LAGB_OK;
+}
+
+// ---- NCCL through dlopen (torch ships libnccl.so.2; no link-time dependency) ----
+struct NcclApi
+{
+   void *lib = nullptr;
+   int (*GetUniqueId)(void *id) = nullptr;
+   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+   int (*GroupStart)() = nullptr;
+   int (*GroupEnd)() = nullptr;
+   int (*CommDestroy)(void*) = nullptr;
+   const char *(*GetErrorString)(int) = nullptr;
+   void *CommInitRankRaw = nullptr;
+};
+struct Uid128 { char internal[128]; };
+static NcclApi g_nccl;
+static int nccl_load()
+{
+   if (g_nccl.lib) { return LAGB_OK; }
+   const char *names[] = {"libnccl.so.2", "libnccl.so"};
+   for (const char *n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) { break; } }
+   if (!g_nccl.lib) { set_error("cannot dlopen libnccl.so.2"); return LAGB_ERR_NCCL; }
+   auto sym = [&](const char *s) { return dlsym(g_nccl.lib, s); };
+   g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+   g_nccl.CommInitRankRaw = sym("ncclCommInitRank");
+   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+   g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+   g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+   g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+   g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+   g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+   g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRankRaw || !g_nccl.AllReduce || !g_nccl.Send || !g_nccl.Recv)
+   { set_error("libnccl: missing symbols"); return LAGB_ERR_NCCL; }
+   return LAGB_OK;
+}
+#define LAGB_NCCL(call) do { int r__ = (call); if (r__ != 0) { \
+   lagb::set_error(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); return LAGB_ERR_NCCL; } } while (0)
+// nccl enums: ncclFloat64 = 8, ncclSum = 0, ncclMin = 3 (stable across NCCL 2.x)
+static const int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;
+
+int allreduce_sum(Ctx &c, double *d_vals, int n)
+{
+   if (c.nranks <= 1) { return LAGB_OK; }
+   LAGB_NCCL(g_nccl.AllReduce(d_vals, d_vals, n, NCCL_F64, NCCL_SUM, c.nccl_comm, c.stream));
+   return LAGB_OK;
+}
+int allreduce_min(Ctx &c, double *d_vals, int n)
+{
+   if (c.nranks <= 1) { return LAGB_OK; }
+   LAGB_NCCL(g_nccl.AllReduce(d_vals, d_vals, n, NCCL_F64, NCCL_MIN, c.nccl_comm, c.stream));
+   return LAGB_OK;
+}
+
+__global__ void halo_pack(int n, int nc, int64_t cstride, const int *__restrict__ idx,
+                          const double *__restrict__ v, double *__restrict__ buf)
+{
+   for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n*nc; i += gridDim.x*blockDim.x)
+   {
+      const int c = i / n, k = i - c*n;
+      buf[i] = v[idx[k] + c*cstride];
+   }
+}
+__global__ void halo_add(int n, int nc, int64_t cstride, const int *__restrict__ idx,
+                         const double *__restrict__ buf, double *__restrict__ v)
+{
+   for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n*nc; i += gridDim.x*blockDim.x)
+   {
+      const int c = i / n, k = i - c*n;
+      v[idx[k] + c*cstride] += buf[i];
+   }
+}
+
+// Sum the partial values of shared dofs over the ranks that share them
+// (P^t then P in the reference's RAP operator, laghos_assembly.cpp:95 / SURVEY 8e):
+// per phase, pack -> grouped ncclSend/ncclRecv -> add.  After all phases every
+// sharing rank holds the same fully summed value.
+int halo_sum(Ctx &c, double *v, int nc)
+{
+   if (c.nranks <= 1 || c.nbrs.empty()) { return LAGB_OK; }
+   for (int ph = 0; ph < c.nphases; ph++)
+   {
+      bool any = false;
+      for (auto &nb : c.nbrs)
+      {
+         if (nb.phase != ph || nb.n == 0) { continue; }
+         any = true;
+         halo_pack<<<std::max(1, std::min(1024, (nb.n*nc + 255)/256)), 256, 0, c.stream>>>(nb.n, nc, c.ndofs, nb.d_idx, v, nb.d_send);
+         LAGB_LAUNCH_CHECK();
+      }
+      if (!any) { continue; }
+      LAGB_NCCL(g_nccl.GroupStart());
+      for (auto &nb : c.nbrs)
+      {
+         if (nb.phase != ph || nb.n == 0) { continue; }
+         LAGB_NCCL(g_nccl.Send(nb.d_send, (size_t)nb.n*nc, NCCL_F64, nb.rank, c.nccl_comm, c.stream));
+         LAGB_NCCL(g_nccl.Recv(nb.d_recv, (size_t)nb.n*nc, NCCL_F64, nb.rank, c.nccl_comm, c.stream));
+      }
+      LAGB_NCCL(g_nccl.GroupEnd());
+      for (auto &nb : c.nbrs)
+      {
+         if (nb.phase != ph || nb.n == 0) { continue; }
+         halo_add<<<std::max(1, std::min(1024, (nb.n*nc + 255)/256)), 256, 0, c.stream>>>(nb.n, nc, c.ndofs, nb.d_idx, nb.d_recv, v);
+         LAGB_LAUNCH_CHECK();
+      }
+   }
+   return LAGB_OK;
+}
+
+__global__ void build_dinvm(int64_t n, int dim, const double *__restrict__ diag, double *__restrict__ dinvm)
+{
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   {
+      const double v = 1.0/diag[i];
+      for (int c = 0; c < dim; c++) { dinvm[i + c*n] = v; }
+   }
+}
+__global__ void neg_inplace(double *y, int64_t n)
+{
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x) { y[i] = -y[i]; }
+}
+
+template<typename T> static int dev_alloc(T **p, size_t n)
+{
+   LAGB_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1)*sizeof(T)));
+   return LAGB_OK;
+}
+template<typename T> static int dev_upload(T **p, const T *h, size_t n)
+{
+   int r = dev_alloc(p, n); if (r) { return r; }
+   if (n) { LAGB_CUDA(cudaMemcpy(*p, h, n*sizeof(T), cudaMemcpyHostToDevice)); }
+   return LAGB_OK;
+}
+
+static int ipow(int a, int b) { int r = 1; while (b-- > 0) { r *= a; } return r; }
+
+// ---------------------------------------------------------------------------
+// PCG driver (MFEM CGSolver::Mult) on device-resident scalars
+// ---------------------------------------------------------------------------
+template<int NC>
+static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, double rel_tol, int max_iter,
+                      bool iterative_mode, int *h_iters)
+{
+   const int64_t n = l2 ? c.ndofs_l2 : c.ndofs;
+   const int64_t cs = n;
+   double *r = l2 ? c.d_lr : c.d_r, *d = l2 ? c.d_ld : c.d_d, *z = l2 ? c.d_lz : c.d_z;
+   const double *dinvm = l2 ? nullptr : c.d_dinvm + (size_t)comp0*c.ndofs;
+   const unsigned char *own = l2 ? nullptr : c.d_own;
+   const int g = vec_grid(n);
+   if (g*NC > c.part_cap) { set_error("pcg: partial buffer too small"); return LAGB_ERR_STATE; }
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+
+   // apply: z (+)= A v ; returns number of partial blocks if the kernel produced d^t A d partials
+   auto apply = [&](const double *v, bool want_den, int &den_blocks) -> int
+   {
+      den_blocks = 0;
+      if (l2) { return ks.mass_l2(c, v, z); }
+      int rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass);
+      if (rc) { return rc; }
+      if (want_den && ks.tuned_mass) { den_blocks = c.dt_nblocks; }
+      return halo_sum(c, z, NC);
+   };
+
+   int rc, den_blocks = 0;
+   if (iterative_mode)
+   {
+      if (!l2) { LAGB_CUDA(cudaMemsetAsync(z, 0, sizeof(double)*NC*n, c.stream)); }
+      rc = apply(x, false, den_blocks); if (rc) { return rc; }
+   }
+   else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
+   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, dinvm, own, r, d, c.d_part, iterative_mode ? 1 : 0);
+   LAGB_LAUNCH_CHECK();
+   pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(g, c.d_part, c.d_tmp);
+   LAGB_LAUNCH_CHECK();
+   rc = allreduce_sum(c, c.d_tmp, NC); if (rc) { return rc; }
+   pcg::finish_init<NC><<<1, 32, 0, c.stream>>>(c.d_state, c.d_tmp, rel_tol, 0.0);
+   LAGB_LAUNCH_CHECK();
+
+   // The host only needs to know when every component has stopped; iterations are
+   // enqueued ahead (kernels skip finished components) and the flag is polled at
+   // a cadence derived from the previous solve's iteration count.
+   int next_check = std::max(1, c.predicted_iters - 1);
+   bool finished = false;
+   int it = 0;
+   auto poll = [&]() -> int
+   {
+      LAGB_CUDA(cudaMemcpyAsync(c.h_state, c.d_state, sizeof(pcg::State), cudaMemcpyDeviceToHost, c.stream));
+      LAGB_CUDA(cudaStreamSynchronize(c.stream));
+      finished = c.h_state->all_done != 0;
+      return LAGB_OK;
+   };
+   if (c.predicted_iters == 0) { rc = poll(); if (rc) { return rc; } }
+   while (!finished && it < max_iter)
+   {
+      it++;
+      rc = apply(d, true, den_blocks); if (rc) { return rc; }
+      if (den_blocks == 0)
+      {
+         pcg::dot_partial<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, d, z, own, c.d_part);
+         LAGB_LAUNCH_CHECK();
+         den_blocks = g;
+      }
+      pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(den_blocks, c.d_part, c.d_tmp);
+      LAGB_LAUNCH_CHECK();
+      rc = allreduce_sum(c, c.d_tmp, NC); if (rc) { return rc; }
+      pcg::finish_den<NC><<<1, 32, 0, c.stream>>>(c.d_state, c.d_tmp, it);
+      LAGB_LAUNCH_CHECK();
+      pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, d, z, dinvm, own, c.d_part);
+      LAGB_LAUNCH_CHECK();
+      pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(g, c.d_part, c.d_tmp + 4);
+      LAGB_LAUNCH_CHECK();
+      rc = allreduce_sum(c, c.d_tmp + 4, NC); if (rc) { return rc; }
+      pcg::finish_beta<NC><<<1, 32, 0, c.stream>>>(c.d_state, c.d_tmp + 4, it, max_iter);
+      LAGB_LAUNCH_CHECK();
+      pcg::update_d<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, d, r, dinvm, z);
+      LAGB_LAUNCH_CHECK();
+      if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
+   }
+   if (!finished) { rc = poll(); if (rc) { return rc; } }
+   int mx = 0;
+   for (int k = 0; k < NC; k++) { h_iters[k] = c.h_state->iters[k]; mx = std::max(mx, h_iters[k]); }
+   c.predicted_iters = mx;
+   return LAGB_OK;
+}
+
+static int pcg_run(Ctx &c, bool l2, int nc, int comp0, const double *b, double *x, double rel_tol,
+                   int max_iter, bool iterative_mode, int *h_iters)
+{
+   switch (nc)
+   {
+      case 1: return pcg_run_nc<1>(c, l2, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters);
+      case 2: return pcg_run_nc<2>(c, l2, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters);
+      case 3: return pcg_run_nc<3>(c, l2, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters);
+   }
+   set_error("pcg: bad component count"); return LAGB_ERR_INVALID;
+}
+
+} // namespace lagb
+
+using namespace lagb;
+
+extern "C" {
+
+const char *lagb_last_error(void) { return g_err.c_str(); }
+int64_t lagb_kernel_launch_count(void) { return g_launch_count; }
+
+struct lagb_ctx { Ctx c; };
+
+int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
+{
+   if (!out || !d) { set_error("ctx_create: null argument"); return LAGB_ERR_INVALID; }
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+   { set_error("no CUDA device: laghos_b200 has no CPU fallback"); return LAGB_ERR_CUDA; }
+   LAGB_CUDA(cudaSetDevice(d->device));
+   lagb_ctx *h = new lagb_ctx();
+   Ctx &c = h->c;
+   c.dim = d->dim; c.NE = d->NE; c.D1D = d->D1D; c.L1D = d->L1D; c.Q1D = d->Q1D;
+   if (c.L1D != c.D1D - 1) { set_error("L1D!=D1D-1"); delete h; return LAGB_ERR_INVALID; } // reference laghos_assembly.cpp:533
+   c.ND = ipow(c.D1D, c.dim); c.NL = ipow(c.L1D, c.dim); c.NQ = ipow(c.Q1D, c.dim);
+   c.ndofs = d->ndofs_h1; c.ndofs_l2 = (int64_t)c.NE*c.NL;
+   c.use_visc = d->use_visc; c.use_vort = d->use_vort; c.variant = d->kernel_variant; c.device = d->device;
+   c.stream = (cudaStream_t)stream;
+   c.ks_generic = make_generic_kernels(c.dim, c.D1D, c.Q1D);
+   if (!c.ks_generic.mass_h1)
+   {
+      char msg[64]; snprintf(msg, sizeof msg, "Unknown kernel 0x%x", (c.dim << 8) | (c.D1D << 4) | c.Q1D);
+      set_error(msg); delete h; return LAGB_ERR_INVALID;
+   }
+   c.ks = c.ks_generic;
+   add_tuned_kernels(c.ks, c.dim, c.D1D, c.Q1D);
+   // tables blob: B | G | BL in DevTables<D1D,Q1D> order
+   const int nb = c.Q1D*c.D1D, nbl = c.Q1D*std::max(1, c.L1D);
+   c.tab_blob.resize(sizeof(double)*(2*nb + nbl));
+   memcpy(c.tab_blob.data(), d->h_B, sizeof(double)*nb);
+   memcpy(c.tab_blob.data() + sizeof(double)*nb, d->h_G, sizeof(double)*nb);
+   memcpy(c.tab_blob.data() + sizeof(double)*2*nb, d->h_BL, sizeof(double)*c.Q1D*c.L1D);
+   int rc = 0;
+   const size_t NEQ = (size_t)c.NE*c.NQ, D2 = (size_t)c.dim*c.dim;
+   rc |= dev_upload(&c.d_map, d->h_h1_map, (size_t)c.NE*c.ND);
+   for (int k = 0; k < c.dim; k++) { c.ness[k] = d->ness[k]; rc |= dev_upload(&c.d_ess[k], d->h_ess[k], (size_t)d->ness[k]); }
+   rc |= dev_upload(&c.d_qweights, d->h_qweights, (size_t)c.NQ);
+   rc |= dev_upload(&c.d_gamma, d->h_gamma, (size_t)c.NE);
+   rc |= dev_alloc(&c.d_sJit, NEQ*D2); rc |= dev_alloc(&c.d_rho0DetJ0w, NEQ);
+   rc |= dev_alloc(&c.d_Jac0inv, NEQ*D2); rc |= dev_alloc(&c.d_massD, NEQ);
+   rc |= dev_alloc(&c.d_diag, (size_t)c.ndofs); rc |= dev_alloc(&c.d_dinvm, (size_t)c.ndofs*c.dim);
+   rc |= dev_alloc(&c.d_r, (size_t)c.ndofs*c.dim); rc |= dev_alloc(&c.d_d, (size_t)c.ndofs*c.dim);
+   rc |= dev_alloc(&c.d_z, (size_t)c.ndofs*c.dim);
+   rc |= dev_alloc(&c.d_lr, (size_t)c.ndofs_l2); rc |= dev_alloc(&c.d_ld, (size_t)c.ndofs_l2);
+   rc |= dev_alloc(&c.d_lz, (size_t)c.ndofs_l2);
+   c.part_cap = std::max(c.NE, 148*16)*4 + 64;
+   rc |= dev_alloc(&c.d_part, (size_t)c.part_cap);
+   rc |= dev_alloc(&c.d_tmp, 16); rc |= dev_alloc(&c.d_dt, 1); rc |= dev_alloc(&c.d_elem_vol, (size_t)c.NE);
+   rc |= dev_alloc(&c.d_state, 1);
+   if (rc) { lagb_ctx_destroy(h); return LAGB_ERR_CUDA; }
+   LAGB_CUDA(cudaMallocHost((void**)&c.h_state, sizeof(pcg::State)));
+   LAGB_CUDA(cudaMallocHost((void**)&c.h_scal, 16*sizeof(double)));
+   LAGB_CUDA(cudaMemset(c.d_sJit, 0, NEQ*D2*sizeof(double)));
+   *out = h;
+   return LAGB_OK;
+}
+
+void lagb_ctx_destroy(lagb_ctx *h)
+{
+   if (!h) { return; }
+   Ctx &c = h->c;
+   cudaStreamSynchronize(c.stream);
+   void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
+                   c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinvm, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
+                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
+   for (void *p : ptrs) { if (p) { cudaFree(p); } }
+   for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
+   if (c.h_state) { cudaFreeHost(c.h_state); }
+   if (c.h_scal) { cudaFreeHost(c.h_scal); }
+   for (int w = 0; w < 4; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
+   for (auto e : c.timer.pool) { cudaEventDestroy(e); }
+   if (c.nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c.nccl_comm); }
+   delete h;
+}
+
+int lagb_ctx_sync(lagb_ctx *h) { LAGB_CUDA(cudaStreamSynchronize(h->c.stream)); return LAGB_OK; }
+
+int lagb_setup_qdata0(lagb_ctx *h, const double *d_x0, const double *d_rho0_gf, const double *d_rho0_q,
+                      int64_t ne_global, double *h0_out)
+{
+   Ctx &c = h->c;
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   int rc = ks.rho0detj0(c, d_x0, d_rho0_gf, d_rho0_q, c.d_elem_vol); if (rc) { return rc; }
+   // volume: fixed-order sum of the per-element volumes (host, once)
+   std::vector<double> ev(c.NE);
+   LAGB_CUDA(cudaMemcpyAsync(ev.data(), c.d_elem_vol, sizeof(double)*c.NE, cudaMemcpyDeviceToHost, c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(c.stream));
+   double vol = 0.0; for (double v : ev) { vol += v; }
+   double ne = (double)c.NE;
+   if (c.nranks > 1)
+   {
+      c.h_scal[0] = vol; c.h_scal[1] = ne;
+      LAGB_CUDA(cudaMemcpyAsync(c.d_tmp, c.h_scal, 2*sizeof(double), cudaMemcpyHostToDevice, c.stream));
+      rc = allreduce_sum(c, c.d_tmp, 2); if (rc) { return rc; }
+      LAGB_CUDA(cudaMemcpyAsync(c.h_scal, c.d_tmp, 2*sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      LAGB_CUDA(cudaStreamSynchronize(c.stream));
+      vol = c.h_scal[0]; ne = c.h_scal[1];
+   }
+   if (ne_global > 0) { ne = (double)ne_global; }
+   c.ne_global = (int64_t)ne;
+   // reference laghos_solver.cpp:253-262 (SQUARE / CUBE)
+   c.h0 = (c.dim == 2) ? sqrt(vol/ne) : pow(vol/ne, 1./3.);
+   c.h0 /= (double)(c.D1D - 1);
+   // Jacobi diagonal (MFEM AssembleDiagonalPA) and its masked inverse per component
+   LAGB_CUDA(cudaMemsetAsync(c.d_diag, 0, sizeof(double)*c.ndofs, c.stream));
+   rc = ks.mass_diag(c, c.d_diag); if (rc) { return rc; }
+   rc = halo_sum(c, c.d_diag, 1); if (rc) { return rc; }
+   build_dinvm<<<vec_grid(c.ndofs), pcg::RB, 0, c.stream>>>(c.ndofs, c.dim, c.d_diag, c.d_dinvm);
+   LAGB_LAUNCH_CHECK();
+   for (int k = 0; k < c.dim; k++)
+   {
+      if (c.ness[k] == 0) { continue; }
+      pcg::vec_zero_idx<<<std::max(1, std::min(1024, (c.ness[k] + 255)/256)), 256, 0, c.stream>>>(c.d_dinvm + (size_t)k*c.ndofs, c.d_ess[k], c.ness[k]);
+      LAGB_LAUNCH_CHECK();
+   }
+   LAGB_CUDA(cudaStreamSynchronize(c.stream));
+   c.setup_done = true;
+   if (h0_out) { *h0_out = c.h0; }
+   return LAGB_OK;
+}
+
+int lagb_vmass_mult(lagb_ctx *h, int comp, const double *d_x, double *d_y)
+{
+   Ctx &c = h->c;
+   if (comp >= c.dim) { set_error("vmass_mult: bad component"); return LAGB_ERR_INVALID; }
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   LAGB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double)*c.ndofs, c.stream));
+   int rc = ks.mass_h1(c, 1, d_x, d_y, false); if (rc) { return rc; }
+   rc = halo_sum(c, d_y, 1); if (rc) { return rc; }
+   if (comp >= 0 && c.ness[comp] > 0)
+   {
+      pcg::vec_zero_idx<<<std::max(1, std::min(1024, (c.ness[comp] + 255)/256)), 256, 0, c.stream>>>(d_y, c.d_ess[comp], c.ness[comp]);
+      LAGB_LAUNCH_CHECK();
+   }
+   return LAGB_OK;
+}
+
+int lagb_vmass_diag(lagb_ctx *h, double *d_diag)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("vmass_diag: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   LAGB_CUDA(cudaMemcpyAsync(d_diag, c.d_diag, sizeof(double)*c.ndofs, cudaMemcpyDeviceToDevice, c.stream));
+   return LAGB_OK;
+}
+
+int lagb_emass_mult(lagb_ctx *h, const double *d_x, double *d_y)
+{
+   Ctx &c = h->c;
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   return ks.mass_l2(c, d_x, d_y);
+}
+
+int lagb_force_mult(lagb_ctx *h, const double *d_e, double *d_v)
+{
+   Ctx &c = h->c;
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   int rc = timer_begin(c, 2); if (rc) { return rc; }
+   LAGB_CUDA(cudaMemsetAsync(d_v, 0, sizeof(double)*c.ndofs*c.dim, c.stream));
+   rc = ks.force_mult(c, d_e, d_v); if (rc) { return rc; }
+   rc = halo_sum(c, d_v, c.dim); if (rc) { return rc; }
+   return timer_end(c, 2);
+}
+
+int lagb_force_mult_transpose(lagb_ctx *h, const double *d_v, double *d_e)
+{
+   Ctx &c = h->c;
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   int rc = timer_begin(c, 2); if (rc) { return rc; }
+   rc = ks.force_mult_t(c, d_v, d_e); if (rc) { return rc; }
+   return timer_end(c, 2);
+}
+
+int lagb_dt_est_set(lagb_ctx *h, double v)
+{
+   Ctx &c = h->c;
+   pcg::vec_fill<<<1, 32, 0, c.stream>>>(c.d_dt, v, 1);
+   LAGB_LAUNCH_CHECK();
+   return LAGB_OK;
+}
+
+int lagb_qupdate_async(lagb_ctx *h, const double *d_S, double cfl)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("qupdate: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   QPointParams prm;
+   prm.h0 = c.h0; prm.h1order = (double)(c.D1D - 1); prm.cfl = cfl; prm.dt_in = std::numeric_limits<double>::infinity();
+   prm.use_viscosity = c.use_visc; prm.use_vorticity = c.use_vort;
+   int rc = timer_begin(c, 3); if (rc) { return rc; }
+   rc = ks.qupdate(c, d_S, prm); if (rc) { return rc; }
+   pcg::vec_min_reduce<<<1, 256, 0, c.stream>>>(c.dt_nblocks, c.d_part, c.d_dt);
+   LAGB_LAUNCH_CHECK();
+   rc = timer_end(c, 3); if (rc) { return rc; }
+   c.quad_tstep += c.NE;
+   return LAGB_OK;
+}
+
+int lagb_dt_est_read(lagb_ctx *h, double *out)
+{
+   Ctx &c = h->c;
+   int rc = allreduce_min(c, c.d_dt, 1); if (rc) { return rc; }
+   LAGB_CUDA(cudaMemcpyAsync(c.h_scal, c.d_dt, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(c.stream));
+   *out = c.h_scal[0];
+   return LAGB_OK;
+}
+
+int lagb_qupdate(lagb_ctx *h, const double *d_S, double cfl, double dt_est_in, double *out)
+{
+   int rc = lagb_dt_est_set(h, dt_est_in); if (rc) { return rc; }
+   rc = lagb_qupdate_async(h, d_S, cfl); if (rc) { return rc; }
+   return lagb_dt_est_read(h, out);
+}
+
+int lagb_pcg_vmass(lagb_ctx *h, int comp, const double *d_b, double *d_x, double rel_tol, int max_iter, int *iters)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("pcg_vmass: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   if (comp < 0 || comp >= c.dim) { set_error("pcg_vmass: bad component"); return LAGB_ERR_INVALID; }
+   int rc = timer_begin(c, 0); if (rc) { return rc; }
+   int it = 0;
+   rc = pcg_run(c, false, 1, comp, d_b, d_x, rel_tol, max_iter, true, &it); if (rc) { return rc; }
+   rc = timer_end(c, 0); if (rc) { return rc; }
+   c.H1iter += it;
+   if (iters) { *iters = it; }
+   return LAGB_OK;
+}
+
+int lagb_pcg_vmass_all(lagb_ctx *h, const double *d_rhs, double *d_dv, double rel_tol, int max_iter, int *iters)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("pcg_vmass_all: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   int rc = timer_begin(c, 0); if (rc) { return rc; }
+   int it[3] = {0, 0, 0};
+   rc = pcg_run(c, false, c.dim, 0, d_rhs, d_dv, rel_tol, max_iter, true, it); if (rc) { return rc; }
+   rc = timer_end(c, 0); if (rc) { return rc; }
+   for (int k = 0; k < c.dim; k++) { c.H1iter += it[k]; if (iters) { iters[k] = it[k]; } }
+   return LAGB_OK;
+}
+
+int lagb_cg_emass(lagb_ctx *h, const double *d_b, double *d_x, double rel_tol, int max_iter, int *iters)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("cg_emass: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   int rc = timer_begin(c, 1); if (rc) { return rc; }
+   int it = 0;
+   const int pred = c.predicted_iters;
+   c.predicted_iters = 0;
+   rc = pcg_run(c, true, 1, 0, d_b, d_x, rel_tol, max_iter, false, &it);
+   c.predicted_iters = pred;
+   if (rc) { return rc; }
+   rc = timer_end(c, 1); if (rc) { return rc; }
+   c.L2iter += (it == 0) ? 1 : it;   // reference laghos_solver.cpp:485-486
+   if (iters) { *iters = it; }
+   return LAGB_OK;
+}
+
+int lagb_taylor_source(lagb_ctx *h, const double *d_x, double *d_esrc)
+{
+   Ctx &c = h->c;
+   if (c.dim != 2) { set_error("taylor_source: 2D only (reference laghos.cpp:638)"); return LAGB_ERR_INVALID; }
+   return c.ks_generic.taylor(c, d_x, d_esrc);
+}
+
+double *lagb_qdata_ptr(lagb_ctx *h, int which)
+{
+   Ctx &c = h->c;
+   switch (which)
+   {
+      case 0: return c.d_sJit; case 1: return c.d_rho0DetJ0w; case 2: return c.d_Jac0inv;
+      case 3: return c.d_massD; case 4: return c.d_diag;
+   }
+   return nullptr;
+}
+double lagb_qdata_h0(const lagb_ctx *h) { return h->c.h0; }
+int lagb_qdata_set_h0(lagb_ctx *h, double h0) { h->c.h0 = h0; return LAGB_OK; }
+
+int lagb_dev_malloc(lagb_ctx *h, double **d_out, int64_t n)
+{
+   (void)h;
+   LAGB_CUDA(cudaMalloc((void**)d_out, std::max<int64_t>(n, 1)*sizeof(double)));
+   return LAGB_OK;
+}
+int lagb_dev_free(lagb_ctx *h, double *p) { (void)h; LAGB_CUDA(cudaFree(p)); return LAGB_OK; }
+int lagb_memcpy_h2d(lagb_ctx *h, double *d_dst, const double *h_src, int64_t n)
+{
+   LAGB_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double)*n, cudaMemcpyHostToDevice, h->c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
+   return LAGB_OK;
+}
+int lagb_memcpy_h2d_async(lagb_ctx *h, double *d_dst, const double *h_src, int64_t n)
+{
+   LAGB_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double)*n, cudaMemcpyHostToDevice, h->c.stream));
+   return LAGB_OK;
+}
+int lagb_memcpy_d2h(lagb_ctx *h, double *h_dst, const double *d_src, int64_t n)
+{
+   LAGB_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double)*n, cudaMemcpyDeviceToHost, h->c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
+   return LAGB_OK;
+}
+int lagb_host_alloc_pinned(double **h_out, int64_t n)
+{
+   LAGB_CUDA(cudaMallocHost((void**)h_out, std::max<int64_t>(n, 1)*sizeof(double)));
+   return LAGB_OK;
+}
+int lagb_host_free_pinned(double *p) { LAGB_CUDA(cudaFreeHost(p)); return LAGB_OK; }
+
+int lagb_vec_fill(lagb_ctx *h, double *y, double a, int64_t n)
+{
+   Ctx &c = h->c;
+   pcg::vec_fill<<<vec_grid(n), pcg::RB, 0, c.stream>>>(y, a, n);
+   LAGB_LAUNCH_CHECK();
+   return LAGB_OK;
+}
+int lagb_vec_copy(lagb_ctx *h, double *y, const double *x, int64_t n)
+{
+   LAGB_CUDA(cudaMemcpyAsync(y, x, sizeof(double)*n, cudaMemcpyDeviceToDevice, h->c.stream));
+   return LAGB_OK;
+}
+int lagb_vec_axpby(lagb_ctx *h, double *z, double a, const double *x, double b, const double *y, int64_t n)
+{
+   Ctx &c = h->c;
+   pcg::vec_axpby<<<vec_grid(n), pcg::RB, 0, c.stream>>>(z, a, x, b, y ? y : x, n);
+   LAGB_LAUNCH_CHECK();
+   return LAGB_OK;
+}
+int lagb_vec_dot(lagb_ctx *h, const double *x, const double *y, int64_t n, double *out)
+{
+   Ctx &c = h->c;
+   const int g = vec_grid(n);
+   pcg::dot_partial<1><<<g, pcg::RB, 0, c.stream>>>(n, 0, x, y, nullptr, c.d_part);
+   LAGB_LAUNCH_CHECK();
+   pcg::reduce_partials<1><<<1, pcg::RB, 0, c.stream>>>(g, c.d_part, c.d_tmp + 8);
+   LAGB_LAUNCH_CHECK();
+   LAGB_CUDA(cudaMemcpyAsync(c.h_scal + 8, c.d_tmp + 8, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(c.stream));
+   *out = c.h_scal[8];
+   return LAGB_OK;
+}
+
+int lagb_nccl_unique_id(uint8_t id_out[128])
+{
+   int rc = nccl_load(); if (rc) { return rc; }
+   LAGB_NCCL(g_nccl.GetUniqueId(id_out));
+   return LAGB_OK;
+}
+
+int lagb_ctx_comm_init(lagb_ctx *h, const uint8_t id[128], int rank, int nranks,
+                       int nnbr, const int32_t *nbr_rank, const int32_t *exchange_phase,
+                       const int32_t *nshared, const int32_t *const *h_shared_dofs,
+                       const uint8_t *h_owner_mask)
+{
+   Ctx &c = h->c;
+   int rc = nccl_load(); if (rc) { return rc; }
+   Uid128 uid; memcpy(uid.internal, id, 128);
+   typedef int (*init_t)(void **, int, Uid128, int);
+   LAGB_NCCL(((init_t)g_nccl.CommInitRankRaw)(&c.nccl_comm, nranks, uid, rank));
+   c.rank = rank; c.nranks = nranks;
+   c.nphases = 0;
+   for (int k = 0; k < nnbr; k++)
+   {
+      Ctx::Nbr nb; nb.rank = nbr_rank[k]; nb.phase = exchange_phase[k]; nb.n = nshared[k];
+      nb.d_idx = nullptr; nb.d_send = nullptr; nb.d_recv = nullptr;
+      rc = dev_upload(&nb.d_idx, (const int*)h_shared_dofs[k], (size_t)nb.n); if (rc) { return rc; }
+      rc = dev_alloc(&nb.d_send, (size_t)nb.n*3); if (rc) { return rc; }
+      rc = dev_alloc(&nb.d_recv, (size_t)nb.n*3); if (rc) { return rc; }
+      c.nbrs.push_back(nb);
+      c.nphases = std::max(c.nphases, nb.phase + 1);
+   }
+   if (h_owner_mask) { rc = dev_upload(&c.d_own, (const unsigned char*)h_owner_mask, (size_t)c.ndofs); if (rc) { return rc; } }
+   return LAGB_OK;
+}
+
+int lagb_allreduce_host(lagb_ctx *h, double *vals, int n, int op)
+{
+   Ctx &c = h->c;
+   if (c.nranks <= 1) { return LAGB_OK; }
+   if (n > 8) { set_error("allreduce_host: n > 8"); return LAGB_ERR_INVALID; }
+   const int nccl_op = (op == 0) ? NCCL_SUM : (op == 1) ? NCCL_MIN : 2 /* ncclMax */;
+   memcpy(c.h_scal, vals, sizeof(double)*n);
+   LAGB_CUDA(cudaMemcpyAsync(c.d_tmp + 8, c.h_scal, sizeof(double)*n, cudaMemcpyHostToDevice, c.stream));
+   LAGB_NCCL(g_nccl.AllReduce(c.d_tmp + 8, c.d_tmp + 8, n, NCCL_F64, nccl_op, c.nccl_comm, c.stream));
+   LAGB_CUDA(cudaMemcpyAsync(c.h_scal, c.d_tmp + 8, sizeof(double)*n, cudaMemcpyDeviceToHost, c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(c.stream));
+   memcpy(vals, c.h_scal, sizeof(double)*n);
+   return LAGB_OK;
+}
+
+int lagb_timing_get(lagb_ctx *h, lagb_timing *out)
+{
+   Ctx &c = h->c;
+   int rc = timer_resolve(c); if (rc) { return rc; }
+   out->t_cgH1 = c.timer.acc[0]; out->t_cgL2 = c.timer.acc[1]; out->t_force = c.timer.acc[2]; out->t_qdata = c.timer.acc[3];
+   out->H1iter = c.H1iter; out->L2iter = c.L2iter; out->quad_tstep = c.quad_tstep;
+   return LAGB_OK;
+}
+int lagb_timing_reset(lagb_ctx *h)
+{
+   Ctx &c = h->c;
+   int rc = timer_resolve(c); if (rc) { return rc; }
+   for (int w = 0; w < 4; w++) { c.timer.acc[w] = 0.0; }
+   c.H1iter = c.L2iter = c.quad_tstep = 0;
+   return LAGB_OK;
+}
+
+} // extern "C"

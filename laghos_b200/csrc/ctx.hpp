@@ -1,0 +1,91 @@
+// Internal context of the C ABI (include/laghos_b200.h).
+#pragma once
+#include "../../include/laghos_b200.h"
+#include "device/pcg.cuh"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace lagb {
+
+void set_error(const std::string &msg);
+extern int64_t g_launch_count;
+
+#define LAGB_CUDA(call) do { cudaError_t err__ = (call); if (err__ != cudaSuccess) { \
+   lagb::set_error(std::string(#call) + ": " + cudaGetErrorString(err__)); return LAGB_ERR_CUDA; } } while (0)
+#define LAGB_LAUNCH_CHECK() do { lagb::g_launch_count++; cudaError_t err__ = cudaGetLastError(); if (err__ != cudaSuccess) { \
+   lagb::set_error(std::string("kernel launch: ") + cudaGetErrorString(err__)); return LAGB_ERR_CUDA; } } while (0)
+
+struct Ctx;
+
+// per-(DIM,D1D,Q1D) launchers
+struct KernelSet
+{
+   int (*mass_h1)(Ctx&, int nc, const double *x, double *y, bool with_den) = nullptr; // y += M x (nc comps, byNODES stride)
+   int (*mass_diag)(Ctx&, double *diag) = nullptr;
+   int (*mass_l2)(Ctx&, const double *x, double *y) = nullptr;
+   int (*force_mult)(Ctx&, const double *e, double *v) = nullptr;       // v += F e
+   int (*force_mult_t)(Ctx&, const double *v, double *e) = nullptr;
+   int (*qupdate)(Ctx&, const double *S, const QPointParams &prm) = nullptr; // writes dt_part, sets dt_nblocks
+   int (*rho0detj0)(Ctx&, const double *x0, const double *rho0_gf, const double *rho0_q, double *elem_vol) = nullptr;
+   int (*taylor)(Ctx&, const double *x, double *esrc) = nullptr;
+   bool tuned_mass = false;
+};
+
+struct Timer
+{
+   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[4];
+   std::vector<cudaEvent_t> pool;
+   double acc[4] = {0, 0, 0, 0}; // cgH1, cgL2, force, qdata (seconds)
+};
+
+struct NcclApi;
+
+struct Ctx
+{
+   int dim = 0, NE = 0, D1D = 0, L1D = 0, Q1D = 0, ND = 0, NL = 0, NQ = 0;
+   int64_t ndofs = 0, ndofs_l2 = 0;
+   int use_visc = 1, use_vort = 0, variant = 0, device = 0;
+   cudaStream_t stream = nullptr;
+   KernelSet ks, ks_generic;
+   std::vector<unsigned char> tab_blob;   // DevTables<D1D,Q1D> bytes
+   // device arrays
+   int *d_map = nullptr; int *d_ess[3] = {nullptr, nullptr, nullptr}; int ness[3] = {0, 0, 0};
+   double *d_qweights = nullptr, *d_gamma = nullptr;
+   double *d_sJit = nullptr, *d_rho0DetJ0w = nullptr, *d_Jac0inv = nullptr, *d_massD = nullptr;
+   double *d_diag = nullptr, *d_dinvm = nullptr;     // [ndofs], [dim*ndofs] (masked)
+   double *d_r = nullptr, *d_d = nullptr, *d_z = nullptr;      // [dim*ndofs]
+   double *d_lr = nullptr, *d_ld = nullptr, *d_lz = nullptr;   // [ndofs_l2]
+   double *d_part = nullptr; int part_cap = 0;                 // reduction partials
+   double *d_tmp = nullptr;                                    // [8] reduced scalars
+   double *d_dt = nullptr;                                     // [1]
+   double *d_elem_vol = nullptr;
+   pcg::State *d_state = nullptr;
+   pcg::State *h_state = nullptr;   // pinned
+   double *h_scal = nullptr;        // pinned [8]
+   unsigned char *d_own = nullptr;  // owner mask (multi-rank), else nullptr
+   double h0 = 0.0;
+   bool setup_done = false;
+   int dt_nblocks = 0;
+   int predicted_iters = 0;
+   // timing
+   Timer timer; int64_t H1iter = 0, L2iter = 0, quad_tstep = 0;
+   // multi-rank
+   int rank = 0, nranks = 1; void *nccl_comm = nullptr;
+   struct Nbr { int rank, phase, n; int *d_idx; double *d_send, *d_recv; };
+   std::vector<Nbr> nbrs; int nphases = 0;
+   int64_t ne_global = 0;
+};
+
+// helpers implemented in capi.cu
+int vec_grid(int64_t n);
+int timer_begin(Ctx &c, int which);
+int timer_end(Ctx &c, int which);
+int halo_sum(Ctx &c, double *v, int nc);              // sum shared dofs across ranks (no-op for 1 rank)
+int allreduce_sum(Ctx &c, double *d_vals, int n);     // in-stream
+int allreduce_min(Ctx &c, double *d_vals, int n);
+
+KernelSet make_generic_kernels(int dim, int D1D, int Q1D);
+bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D);
+
+} // namespace lagb

@@ -1,0 +1,273 @@
+// Device-resident (P)CG: MFEM CGSolver::Mult restated (call
+// sites reference laghos_solver.cpp:388 and :481) with all scalars (nom, den,
+// alpha, beta, r0, convergence flags) kept in device memory so that an iteration is
+// a fixed sequence of kernel launches with no host round trip; NC independent
+// systems (the `dim` velocity components) advance in lock-step and share one pass
+// over the operator's quadrature data.
+//
+// Essential dofs: the Jacobi inverse diagonal `dinvm` is zero at the component's
+// essential dofs, which keeps d, and therefore x, exactly zero there; entries of r
+// and z at those dofs are never used (they are multiplied by zero), which is
+// arithmetically identical to zeroing the operator rows and the RHS entries
+// (MassPAOperator::Mult / EliminateRHS, reference laghos_assembly.cpp:112-121).
+//
+// All reductions are two-stage with fixed summation order (deterministic).
+#pragma once
+#include "common.cuh"
+
+namespace lagb {
+namespace pcg {
+
+constexpr int MAXC = 3;
+constexpr int RB = 256;       // reduction / vector kernel block size
+
+struct State                  // lives in device memory
+{
+   double nom[MAXC], den[MAXC], betanom[MAXC], r0[MAXC], alpha[MAXC], beta[MAXC];
+   int done[MAXC];            // 1 once the component has stopped iterating
+   int iters[MAXC];           // MFEM final_iter
+   int all_done;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+   for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+   const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+   __syncthreads();
+   if ((threadIdx.x & 31) == 0) { sh[w] = v; }
+   __syncthreads();
+   double s = 0.0;
+   if (threadIdx.x == 0) { for (int i = 0; i < nw; i++) { s += sh[i]; } }
+   return s;   // valid on thread 0
+}
+
+// r = b - z (z = A x), zz = dinvm*r, d = zz, nom_part = sum own*zz*r ; z = 0
+template<int NC>
+__global__ void init_residual(int64_t n, int64_t cstride, const double *__restrict__ b, double *__restrict__ z,
+                              const double *__restrict__ dinvm, const unsigned char *__restrict__ own,
+                              double *__restrict__ r, double *__restrict__ d, double *__restrict__ part,
+                              int iterative_mode)
+{
+   __shared__ double sh[32];
+   double acc[NC];
+#pragma unroll
+   for (int c = 0; c < NC; c++) { acc[c] = 0.0; }
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   {
+      const double w = own ? (double)own[i] : 1.0;
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+      {
+         const int64_t k = i + c*cstride;
+         const double rr = iterative_mode ? b[k] - z[k] : b[k];
+         const double zz = dinvm ? dinvm[k]*rr : rr;
+         r[k] = rr; d[k] = zz; z[k] = 0.0;
+         acc[c] += w*zz*rr;
+      }
+   }
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+   {
+      const double s = block_sum(acc[c], sh);
+      if (threadIdx.x == 0) { part[(size_t)blockIdx.x*NC + c] = s; }
+   }
+}
+
+// generic partial dot: part[b*NC + c] = sum own*x*y
+template<int NC>
+__global__ void dot_partial(int64_t n, int64_t cstride, const double *__restrict__ x, const double *__restrict__ y,
+                            const unsigned char *__restrict__ own, double *__restrict__ part)
+{
+   __shared__ double sh[32];
+   double acc[NC];
+#pragma unroll
+   for (int c = 0; c < NC; c++) { acc[c] = 0.0; }
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   {
+      const double w = own ? (double)own[i] : 1.0;
+#pragma unroll
+      for (int c = 0; c < NC; c++) { acc[c] += w*x[i + c*cstride]*y[i + c*cstride]; }
+   }
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+   {
+      const double s = block_sum(acc[c], sh);
+      if (threadIdx.x == 0) { part[(size_t)blockIdx.x*NC + c] = s; }
+   }
+}
+
+// out[c] = sum_b part[b*NC + c], fixed order; one block.
+template<int NC>
+__global__ void reduce_partials(int nblocks, const double *__restrict__ part, double *__restrict__ out)
+{
+   __shared__ double sh[32];
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+   {
+      double a = 0.0;
+      for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { a += part[(size_t)b*NC + c]; }
+      const double s = block_sum(a, sh);
+      if (threadIdx.x == 0) { out[c] = s; }
+   }
+}
+
+// after the initial nom reduction (and allreduce): st.nom holds the sum in `tmp`
+template<int NC>
+__global__ void finish_init(State *st, const double *tmp, double rel_tol, double abs_tol)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+   int all = 1;
+   for (int c = 0; c < NC; c++)
+   {
+      const double nom = tmp[c];
+      st->nom[c] = nom;
+      st->iters[c] = 0;
+      st->done[c] = 0;
+      if (nom < 0.0) { st->done[c] = 1; }   // not positive definite: MFEM returns, final_iter = 0
+      const double r0 = fmax(nom*rel_tol*rel_tol, abs_tol*abs_tol);
+      st->r0[c] = r0;
+      if (nom <= r0) { st->done[c] = 1; }
+      all &= st->done[c];
+   }
+   st->all_done = all;
+}
+
+// den reduced into tmp: alpha = nom/den
+template<int NC>
+__global__ void finish_den(State *st, const double *tmp, int iter)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+   for (int c = 0; c < NC; c++)
+   {
+      if (st->done[c]) { continue; }
+      const double den = tmp[c];
+      st->den[c] = den;
+      if (den == 0.0)
+      {
+         // MFEM: stop, final_iter = current iteration index (0 before the loop)
+         st->done[c] = 1; st->iters[c] = iter - 1; st->alpha[c] = 0.0;
+         continue;
+      }
+      st->alpha[c] = st->nom[c]/den;
+   }
+}
+
+// x += alpha d ; r -= alpha z ; betanom_part = sum own*r*(dinvm*r)
+template<int NC>
+__global__ void update_xr(int64_t n, int64_t cstride, const State *__restrict__ st,
+                          double *__restrict__ x, double *__restrict__ r, const double *__restrict__ d,
+                          const double *__restrict__ z, const double *__restrict__ dinvm,
+                          const unsigned char *__restrict__ own, double *__restrict__ part)
+{
+   __shared__ double sh[32];
+   double acc[NC], alpha[NC]; bool skip[NC];
+#pragma unroll
+   for (int c = 0; c < NC; c++) { acc[c] = 0.0; alpha[c] = st->alpha[c]; skip[c] = st->done[c] != 0; }
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   {
+      const double w = own ? (double)own[i] : 1.0;
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+      {
+         if (skip[c]) { continue; }
+         const int64_t k = i + c*cstride;
+         x[k] = x[k] + alpha[c]*d[k];
+         const double rr = r[k] - alpha[c]*z[k];
+         r[k] = rr;
+         const double zz = dinvm ? dinvm[k]*rr : rr;
+         acc[c] += w*rr*zz;
+      }
+   }
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+   {
+      const double s = block_sum(acc[c], sh);
+      if (threadIdx.x == 0) { part[(size_t)blockIdx.x*NC + c] = s; }
+   }
+}
+
+// betanom reduced into tmp: convergence test, beta, nom <- betanom
+template<int NC>
+__global__ void finish_beta(State *st, const double *tmp, int iter, int max_iter)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+   int all = 1;
+   for (int c = 0; c < NC; c++)
+   {
+      if (!st->done[c])
+      {
+         const double betanom = tmp[c];
+         st->betanom[c] = betanom;
+         if (betanom < 0.0 || betanom <= st->r0[c]) { st->done[c] = 1; st->iters[c] = iter; }
+         else if (iter >= max_iter) { st->done[c] = 1; st->iters[c] = max_iter; }
+         else
+         {
+            st->beta[c] = betanom/st->nom[c];
+            st->nom[c] = betanom;
+         }
+      }
+      all &= st->done[c];
+   }
+   st->all_done = all;
+}
+
+// d = dinvm*r + beta d ; z = 0   (skipped for finished components)
+template<int NC>
+__global__ void update_d(int64_t n, int64_t cstride, const State *__restrict__ st,
+                         double *__restrict__ d, const double *__restrict__ r,
+                         const double *__restrict__ dinvm, double *__restrict__ z)
+{
+   double beta[NC]; bool skip[NC];
+#pragma unroll
+   for (int c = 0; c < NC; c++) { beta[c] = st->beta[c]; skip[c] = st->done[c] != 0; }
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   {
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+      {
+         const int64_t k = i + c*cstride;
+         if (!skip[c])
+         {
+            const double zz = dinvm ? dinvm[k]*r[k] : r[k];
+            d[k] = zz + beta[c]*d[k];
+         }
+         z[k] = 0.0;
+      }
+   }
+}
+
+// ---- plain vector kernels (shim Vector ops, RK stage combinations) ----
+static __global__ void vec_fill(double *__restrict__ y, double a, int64_t n)
+{
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x) { y[i] = a; }
+}
+static __global__ void vec_axpby(double *__restrict__ z, double a, const double *__restrict__ x, double b,
+                          const double *__restrict__ y, int64_t n)
+{
+   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   {
+      z[i] = (b == 0.0) ? a*x[i] : a*x[i] + b*y[i];
+   }
+}
+static __global__ void vec_zero_idx(double *__restrict__ y, const int *__restrict__ idx, int n)
+{
+   for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) { y[idx[i]] = 0.0; }
+}
+// inout[0] = min(inout[0], min_i part[i])
+static __global__ void vec_min_reduce(int n, const double *__restrict__ part, double *__restrict__ out)
+{
+   __shared__ double sh[32];
+   double m = out[0];
+   for (int i = threadIdx.x; i < n; i += blockDim.x) { m = fmin(m, part[i]); }
+   for (int o = 16; o > 0; o >>= 1) { m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+   if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = m; }
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      for (int w = 1; w < (blockDim.x + 31)/32; w++) { m = fmin(m, sh[w]); }
+      out[0] = m;
+   }
+}
+
+} // namespace pcg
+} // namespace lagb

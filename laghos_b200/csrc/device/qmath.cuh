@@ -1,0 +1,268 @@
+// Device 2x2 / 3x3 dense helpers for the quadrature-point physics (QUpdate).
+//
+// Same algorithms as MFEM's linalg/kernels.hpp routines that the reference's
+// QUpdateBody calls (reference laghos_solver.cpp:1078-1158): determinant and
+// adjugate inverse, scaled closed-form symmetric eigen-solver (trigonometric root
+// of the characteristic polynomial that is best separated, deflation by its
+// eigenvector, Parlett's 2x2 rotation), smallest singular value through the
+// eigenvalues of J^t J.  QUpdateBody only consumes the smallest eigenvalue and its
+// eigenvector (compr_dir, laghos_solver.cpp:1113-1124), so only that pair is
+// returned.  Written with scalars and selects (no dynamically indexed arrays) so
+// everything stays in registers.  Column-major like MFEM.
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+
+namespace lagb {
+namespace qm {
+
+#define LAGB_HD __host__ __device__ __forceinline__
+
+LAGB_HD double scaling_factor(double d_max)
+{
+   if (d_max > 0.0)
+   {
+      int e; double m = frexp(d_max, &e);
+      if (e == DBL_MAX_EXP) { m *= 2.0; }
+      return d_max/m;
+   }
+   return 1.0;
+}
+
+// Parlett: rotation diagonalising [d1 d12; d12 d2]; eigenvectors (c,-s), (s,c)
+LAGB_HD void eigensystem2s(const double d12, double &d1, double &d2, double &c, double &s)
+{
+   const double sqrt_1_eps = 67108864.0; // sqrt(1/DBL_EPSILON) = 2^26
+   if (d12 == 0.0) { c = 1.0; s = 0.0; return; }
+   double t;
+   const double zeta = (d2 - d1)/(2*d12);
+   const double azeta = fabs(zeta);
+   if (azeta < sqrt_1_eps) { t = copysign(1.0/(azeta + sqrt(1.0 + zeta*zeta)), zeta); }
+   else { t = copysign(0.5/azeta, zeta); }
+   c = sqrt(1.0/(1.0 + t*t));
+   s = c*t;
+   t *= d12;
+   d1 -= t;
+   d2 += t;
+}
+
+// unit vector in the near-kernel of the symmetric [c1 d12 d13; d12 c2 d23; d13 d23 c3]
+LAGB_HD bool kernel_vector3s(double c1, double c2, double c3, double d12, double d13, double d23,
+                             double &z0, double &z1, double &z2)
+{
+   // cross products of the row pairs (r0,r1), (r0,r2), (r1,r2)
+   const double a0 = d12*d23 - d13*c2,  a1 = d13*d12 - c1*d23,  a2 = c1*c2 - d12*d12;
+   const double b0 = d12*c3 - d13*d23,  b1 = d13*d13 - c1*c3,   b2 = c1*d23 - d12*d13;
+   const double e0 = c2*c3 - d23*d23,   e1 = d23*d13 - d12*c3,  e2 = d12*d23 - c2*d13;
+   const double na = a0*a0 + a1*a1 + a2*a2;
+   const double nb = b0*b0 + b1*b1 + b2*b2;
+   const double ne = e0*e0 + e1*e1 + e2*e2;
+   double n = na; z0 = a0; z1 = a1; z2 = a2;
+   if (nb > n) { n = nb; z0 = b0; z1 = b1; z2 = b2; }
+   if (ne > n) { n = ne; z0 = e0; z1 = e1; z2 = e2; }
+   const double amax = fmax(fmax(fmax(fabs(c1), fabs(c2)), fmax(fabs(c3), fabs(d12))), fmax(fabs(d13), fabs(d23)));
+   if (!(n > 1e-28*amax*amax*amax*amax) || n == 0.0) { return false; }
+   const double inv = 1.0/sqrt(n);
+   z0 *= inv; z1 *= inv; z2 *= inv;
+   return true;
+}
+
+// Householder completion: u, w orthonormal and orthogonal to the unit vector z
+LAGB_HD void complete_basis(double z0, double z1, double z2,
+                            double &u0, double &u1, double &u2, double &w0, double &w1, double &w2)
+{
+   int k = 0; double zk = z0;
+   if (fabs(z1) < fabs(zk)) { k = 1; zk = z1; }
+   if (fabs(z2) < fabs(zk)) { k = 2; zk = z2; }
+   const double sgn = (zk >= 0.) ? 1.0 : -1.0;
+   const double v0 = z0 + (k == 0 ? sgn : 0.0);
+   const double v1 = z1 + (k == 1 ? sgn : 0.0);
+   const double v2 = z2 + (k == 2 ? sgn : 0.0);
+   const double vn2 = v0*v0 + v1*v1 + v2*v2;
+   // i1 = (k+1)%3, i2 = (k+2)%3
+   const double vi1 = (k == 0) ? v1 : (k == 1) ? v2 : v0;
+   const double vi2 = (k == 0) ? v2 : (k == 1) ? v0 : v1;
+   const int i1 = (k + 1) % 3, i2 = (k + 2) % 3;
+   u0 = ((i1 == 0) ? 1.0 : 0.0) - 2.0*v0*vi1/vn2;
+   u1 = ((i1 == 1) ? 1.0 : 0.0) - 2.0*v1*vi1/vn2;
+   u2 = ((i1 == 2) ? 1.0 : 0.0) - 2.0*v2*vi1/vn2;
+   w0 = ((i2 == 0) ? 1.0 : 0.0) - 2.0*v0*vi2/vn2;
+   w1 = ((i2 == 1) ? 1.0 : 0.0) - 2.0*v1*vi2/vn2;
+   w2 = ((i2 == 2) ? 1.0 : 0.0) - 2.0*v2*vi2/vn2;
+}
+
+// smallest eigenvalue and its unit eigenvector of the symmetric 2x2 (a d; d b)
+LAGB_HD void min_eig2(double a, double d, double b, double &lmin, double &x0, double &x1)
+{
+   double c, s;
+   eigensystem2s(d, a, b, c, s);
+   if (a <= b) { lmin = a; x0 = c; x1 = -s; }
+   else        { lmin = b; x0 = s; x1 = c; }
+}
+
+// smallest eigenvalue and its unit eigenvector of the symmetric 3x3 with entries
+// (d11 d12 d13; . d22 d23; . . d33)
+LAGB_HD void min_eig3(double d11, double d12, double d13, double d22, double d23, double d33,
+                      double &lmin, double &x0, double &x1, double &x2)
+{
+   const double d_max = fmax(fmax(fmax(fabs(d11), fabs(d22)), fmax(fabs(d33), fabs(d12))), fmax(fabs(d13), fabs(d23)));
+   const double mult = scaling_factor(d_max);
+   d11 /= mult; d22 /= mult; d33 /= mult;
+   d12 /= mult; d13 /= mult; d23 /= mult;
+   double aa = (d11 + d22 + d33)/3;
+   double c1 = d11 - aa, c2 = d22 - aa, c3 = d33 - aa;
+   const double Q = (2*(d12*d12 + d13*d13 + d23*d23) + c1*c1 + c2*c2 + c3*c3)/6;
+   double R = (c1*(d23*d23 - c2*c3) + d12*(d12*c3 - 2*d13*d23) + d13*d13*c2)/2;
+   bool ident = true;
+   if (Q > 0.)
+   {
+      const double sqrtQ = sqrt(Q);
+      const double sqrtQ3 = Q*sqrtQ;
+      double r;
+      if (fabs(R) >= sqrtQ3) { r = (R < 0.) ? 2*sqrtQ : -2*sqrtQ; }
+      else
+      {
+         R = R/sqrtQ3;
+         if (R < 0.) { r = -2*sqrtQ*cos((acos(R) + 2.0*M_PI)/3); }
+         else        { r = -2*sqrtQ*cos(acos(R)/3); }
+      }
+      aa += r;
+      c1 = d11 - aa; c2 = d22 - aa; c3 = d33 - aa;
+      double z0, z1, z2;
+      if (kernel_vector3s(c1, c2, c3, d12, d13, d23, z0, z1, z2))
+      {
+         ident = false;
+         double u0, u1, u2, w0, w1, w2;
+         complete_basis(z0, z1, z2, u0, u1, u2, w0, w1, w2);
+         const double Az0 = d11*z0 + d12*z1 + d13*z2, Az1 = d12*z0 + d22*z1 + d23*z2, Az2 = d13*z0 + d23*z1 + d33*z2;
+         const double Au0 = d11*u0 + d12*u1 + d13*u2, Au1 = d12*u0 + d22*u1 + d23*u2, Au2 = d13*u0 + d23*u1 + d33*u2;
+         const double Aw0 = d11*w0 + d12*w1 + d13*w2, Aw1 = d12*w0 + d22*w1 + d23*w2, Aw2 = d13*w0 + d23*w1 + d33*w2;
+         const double l1 = z0*Az0 + z1*Az1 + z2*Az2;
+         double b22 = u0*Au0 + u1*Au1 + u2*Au2;
+         double b33 = w0*Aw0 + w1*Aw1 + w2*Aw2;
+         const double b23 = u0*Aw0 + u1*Aw1 + u2*Aw2;
+         double c, s;
+         eigensystem2s(b23, b22, b33, c, s);
+         // stable ascending selection among (l1, b22, b33)
+         lmin = l1; x0 = z0; x1 = z1; x2 = z2;
+         if (b22 < lmin) { lmin = b22; x0 = c*u0 - s*w0; x1 = c*u1 - s*w1; x2 = c*u2 - s*w2; }
+         if (b33 < lmin) { lmin = b33; x0 = s*u0 + c*w0; x1 = s*u1 + c*w1; x2 = s*u2 + c*w2; }
+      }
+   }
+   if (ident) { lmin = aa; x0 = 1.0; x1 = 0.0; x2 = 0.0; }
+   lmin *= mult;
+}
+
+// smallest singular value of the 2x2 column-major (d0 d2; d1 d3)
+LAGB_HD double min_sv2(double d0, double d1, double d2, double d3)
+{
+   const double d_max = fmax(fmax(fabs(d0), fabs(d1)), fmax(fabs(d2), fabs(d3)));
+   const double mult = scaling_factor(d_max);
+   d0 /= mult; d1 /= mult; d2 /= mult; d3 /= mult;
+   double t = 0.5*((d0 + d2)*(d0 - d2) + (d1 - d3)*(d1 + d3));
+   double s = d0*d2 + d1*d3;
+   s = sqrt(0.5*(d0*d0 + d1*d1 + d2*d2 + d3*d3) + sqrt(t*t + s*s));
+   if (s == 0.0) { return 0.0; }
+   t = fabs(d0*d3 - d1*d2)/s;
+   if (t > s) { return s*mult; }
+   return t*mult;
+}
+
+// smallest singular value of the 3x3 column-major J (d0..d8)
+LAGB_HD double min_sv3(double d0, double d1, double d2, double d3, double d4,
+                       double d5, double d6, double d7, double d8)
+{
+   double d_max = fmax(fmax(fmax(fabs(d0), fabs(d1)), fmax(fabs(d2), fabs(d3))),
+                       fmax(fmax(fabs(d4), fabs(d5)), fmax(fabs(d6), fmax(fabs(d7), fabs(d8)))));
+   const double mult = scaling_factor(d_max);
+   d0 /= mult; d1 /= mult; d2 /= mult; d3 /= mult; d4 /= mult;
+   d5 /= mult; d6 /= mult; d7 /= mult; d8 /= mult;
+   const double b11 = d0*d0 + d1*d1 + d2*d2;
+   const double b12 = d0*d3 + d1*d4 + d2*d5;
+   const double b13 = d0*d6 + d1*d7 + d2*d8;
+   const double b22 = d3*d3 + d4*d4 + d5*d5;
+   const double b23 = d3*d6 + d4*d7 + d5*d8;
+   const double b33 = d6*d6 + d7*d7 + d8*d8;
+   double aa = (b11 + b22 + b33)/3;
+   const double b11_b22 = ((d0 - d3)*(d0 + d3) + (d1 - d4)*(d1 + d4) + (d2 - d5)*(d2 + d5));
+   const double b22_b33 = ((d3 - d6)*(d3 + d6) + (d4 - d7)*(d4 + d7) + (d5 - d8)*(d5 + d8));
+   const double b33_b11 = ((d6 - d0)*(d6 + d0) + (d7 - d1)*(d7 + d1) + (d8 - d2)*(d8 + d2));
+   const double c1 = (b11_b22 - b33_b11)/3;
+   const double c2 = (b22_b33 - b11_b22)/3;
+   const double c3 = (b33_b11 - b22_b33)/3;
+   const double Q = (2*(b12*b12 + b13*b13 + b23*b23) + c1*c1 + c2*c2 + c3*c3)/6;
+   double R = (c1*(b23*b23 - c2*c3) + b12*(b12*c3 - 2*b13*b23) + b13*b13*c2)/2;
+   if (Q > 0.)
+   {
+      const double sqrtQ = sqrt(Q);
+      const double sqrtQ3 = Q*sqrtQ;
+      double r = 0.0;
+      bool have_aa = false;
+      if (fabs(R) >= sqrtQ3) { r = (R < 0.) ? 2*sqrtQ : -2*sqrtQ; }
+      else
+      {
+         R = R/sqrtQ3;
+         if (fabs(R) <= 0.9) { aa -= 2*sqrtQ*cos(acos(R)/3); have_aa = true; }
+         else if (R < 0.) { r = -2*sqrtQ*cos((acos(R) + 2.0*M_PI)/3); }
+         else { r = -2*sqrtQ*cos(acos(R)/3); aa += r; have_aa = true; }
+      }
+      if (!have_aa)
+      {
+         const double l1 = aa + r;
+         double z0, z1, z2;
+         if (!kernel_vector3s(b11 - l1, b22 - l1, b33 - l1, b12, b13, b23, z0, z1, z2)) { aa = l1; }
+         else
+         {
+            double u0, u1, u2, w0, w1, w2;
+            complete_basis(z0, z1, z2, u0, u1, u2, w0, w1, w2);
+            const double Bz0 = b11*z0 + b12*z1 + b13*z2, Bz1 = b12*z0 + b22*z1 + b23*z2, Bz2 = b13*z0 + b23*z1 + b33*z2;
+            const double Bu0 = b11*u0 + b12*u1 + b13*u2, Bu1 = b12*u0 + b22*u1 + b23*u2, Bu2 = b13*u0 + b23*u1 + b33*u2;
+            const double Bw0 = b11*w0 + b12*w1 + b13*w2, Bw1 = b12*w0 + b22*w1 + b23*w2, Bw2 = b13*w0 + b23*w1 + b33*w2;
+            const double e1 = z0*Bz0 + z1*Bz1 + z2*Bz2;
+            double e2 = u0*Bu0 + u1*Bu1 + u2*Bu2;
+            double e3 = w0*Bw0 + w1*Bw1 + w2*Bw2;
+            const double e23 = u0*Bw0 + u1*Bw1 + u2*Bw2;
+            double c, s;
+            eigensystem2s(e23, e2, e3, c, s);
+            aa = fmin(fmin(e1, e2), e3);
+         }
+      }
+   }
+   return sqrt(fabs(aa))*mult;
+}
+
+// MFEM kernels::Norml2 (scaled 2-norm), sizes 2 and 3
+LAGB_HD double norml2_accum(double &scale, double &sum, double v)
+{
+   if (v != 0.0)
+   {
+      const double a = fabs(v);
+      if (scale <= a) { const double q = scale/a; sum = 1.0 + sum*(q*q); scale = a; }
+      else { const double q = a/scale; sum += q*q; }
+   }
+   return 0.0;
+}
+LAGB_HD double norml2_2(double a, double b)
+{
+   double scale = 0.0, sum = 0.0;
+   norml2_accum(scale, sum, a); norml2_accum(scale, sum, b);
+   return scale*sqrt(sum);
+}
+LAGB_HD double norml2_3(double a, double b, double c)
+{
+   double scale = 0.0, sum = 0.0;
+   norml2_accum(scale, sum, a); norml2_accum(scale, sum, b); norml2_accum(scale, sum, c);
+   return scale*sqrt(sum);
+}
+
+LAGB_HD double smooth_step_01(double x, double eps)
+{
+   const double y = (x + eps)/(2.0*eps);
+   if (y < 0.0) { return 0.0; }
+   if (y > 1.0) { return 1.0; }
+   return (3.0 - 2.0*y)*y*y;
+}
+
+} // namespace qm
+} // namespace lagb

@@ -252,7 +252,9 @@ struct ICs
 struct Problem
 {
    ProblemSpec spec;
-   RectMesh mesh;
+   RectMesh mesh;          // the GLOBAL mesh
+   int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};   // this rank's element box [lo,hi) per axis
+   int nloc[3] = {1, 1, 1};                    // hi - lo
    Tables1D tab;
    int dim = 3, NE = 0, D1D = 0, L1D = 0, Q1D = 0;
    int ND = 0;      // H1 dofs per element  D1D^dim
@@ -276,26 +278,44 @@ struct Problem
 
    static int ipow(int a, int b) { int r = 1; while (b-- > 0) { r *= a; } return r; }
 
-   // reference-coordinates -> physical for element (ix,iy,iz)
-   void elem_box(int e, double *lo, double *hi) const
+   // global element index (per axis) of local element e
+   void elem_idx(int e, int *idx) const
    {
-      int idx[3];
-      idx[0] = e % mesh.n[0]; idx[1] = (e/mesh.n[0]) % mesh.n[1];
-      idx[2] = e/(mesh.n[0]*mesh.n[1]);
+      idx[0] = lo[0] + e % nloc[0]; idx[1] = lo[1] + (e/nloc[0]) % nloc[1];
+      idx[2] = lo[2] + e/(nloc[0]*nloc[1]);
+   }
+   // physical box of local element e
+   void elem_box(int e, double *blo, double *bhi) const
+   {
+      int idx[3]; elem_idx(e, idx);
       for (int d = 0; d < 3; d++)
       {
-         lo[d] = mesh.brk[d][idx[d]]; hi[d] = mesh.brk[d][idx[d]+1];
+         blo[d] = mesh.brk[d][idx[d]]; bhi[d] = mesh.brk[d][idx[d]+1];
       }
    }
 
+   // whole mesh on one rank
    void build(const ProblemSpec &sp, const RectMesh &m)
    {
+      const int l0[3] = {0, 0, 0};
+      build(sp, m, l0, m.n);
+   }
+
+   // element box [lo_,hi_) of the global mesh m (element-partitioned ranks):
+   // boundary conditions and the Sedov delta refer to the GLOBAL mesh.
+   void build(const ProblemSpec &sp, const RectMesh &m, const int *lo_, const int *hi_)
+   {
       spec = sp; mesh = m; dim = m.dim;
+      for (int d = 0; d < 3; d++)
+      {
+         lo[d] = (d < dim) ? lo_[d] : 0; hi[d] = (d < dim) ? hi_[d] : 1; nloc[d] = hi[d] - lo[d];
+         if (nloc[d] < 1 || lo[d] < 0 || hi[d] > m.n[d]) { throw std::runtime_error("bad element box"); }
+      }
       tab.build(sp.ok, sp.ot, sp.oq);
       D1D = tab.D1D; L1D = tab.L1D; Q1D = tab.Q1D;
       ND = ipow(D1D, dim); NL = ipow(L1D, dim); NQ = ipow(Q1D, dim);
-      NE = mesh.NE();
-      for (int d = 0; d < 3; d++) { N1[d] = (d < dim) ? mesh.n[d]*sp.ok + 1 : 1; }
+      NE = nloc[0]*nloc[1]*nloc[2];
+      for (int d = 0; d < 3; d++) { N1[d] = (d < dim) ? nloc[d]*sp.ok + 1 : 1; }
       ndofs_h1 = (int64_t)N1[0]*N1[1]*N1[2];
       ndofs_l2 = (int64_t)NE*NL;
       if (ndofs_h1*dim > 2000000000LL) { throw std::runtime_error("mesh too large for int32 dof ids"); }
@@ -315,8 +335,8 @@ struct Problem
       const int DZ = (dim == 3) ? D1D : 1;
       for (int e = 0; e < NE; e++)
       {
-         const int ix = e % mesh.n[0], iy = (e/mesh.n[0]) % mesh.n[1];
-         const int iz = e/(mesh.n[0]*mesh.n[1]);
+         const int ix = e % nloc[0], iy = (e/nloc[0]) % nloc[1];
+         const int iz = e/(nloc[0]*nloc[1]);
          for (int kz = 0; kz < DZ; kz++)
             for (int ky = 0; ky < D1D; ky++)
                for (int kx = 0; kx < D1D; kx++)
@@ -334,7 +354,8 @@ struct Problem
                for (int gx = 0; gx < N1[0]; gx++)
                {
                   const int g[3] = {gx, gy, gz};
-                  if (g[c] == 0 || g[c] == N1[c] - 1) { ess[c].push_back(gx + N1[0]*(gy + N1[1]*gz)); }
+                  const int gg = lo[c]*sp.ok + g[c];   // global lattice index
+                  if (gg == 0 || gg == mesh.n[c]*sp.ok) { ess[c].push_back(gx + N1[0]*(gy + N1[1]*gz)); }
                }
       }
       // tensor quadrature weights, q = qx + Q1D*(qy + Q1D*qz)
@@ -356,20 +377,23 @@ struct Problem
             {
                const int g[3] = {gx, gy, gz};
                double x[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+               bool on_bdr[3] = {false, false, false};
                for (int d = 0; d < dim; d++)
                {
-                  const int el = std::min(g[d]/sp.ok, mesh.n[d] - 1);
-                  const int j = g[d] - el*sp.ok;
+                  const int ell = std::min(g[d]/sp.ok, nloc[d] - 1);
+                  const int j = g[d] - ell*sp.ok;
+                  const int el = lo[d] + ell;
                   const double a = mesh.brk[d][el], b = mesh.brk[d][el+1];
                   x[d] = (j == 0) ? a : (j == sp.ok) ? b : a + (b - a)*tab.gll[j];
+                  const int gg = lo[d]*sp.ok + g[d];
+                  on_bdr[d] = (gg == 0 || gg == mesh.n[d]*sp.ok);
                }
                ic.v0(x, v);
                const int64_t id = gx + (int64_t)N1[0]*(gy + (int64_t)N1[1]*gz);
                for (int d = 0; d < dim; d++)
                {
                   X[d*ndofs_h1 + id] = x[d];
-                  const bool on_bdr = (g[d] == 0 || g[d] == N1[d] - 1);
-                  V[d*ndofs_h1 + id] = on_bdr ? 0.0 : v[d];
+                  V[d*ndofs_h1 + id] = on_bdr[d] ? 0.0 : v[d];
                }
             }
 
@@ -391,14 +415,38 @@ struct Problem
             if (fabs(mesh.brk[d][i]) < best) { best = fabs(mesh.brk[d][i]); vnear[d] = (int)i; }
          }
       }
+      // unit-weight mass integral of the nodal interpolant over ALL (global) elements
+      // that own the vertex: sum_q w detJ f(q); f is a tensor polynomial of degree ot,
+      // so Gauss-Legendre(Q1D) is exact.
       double delta_integral = 0.0;
-      std::vector<char> delta_elem(NE, 0);
+      if (sp.problem == 1)
+      {
+         const int ncand = 1 << dim;
+         for (int k = 0; k < ncand; k++)
+         {
+            double integ = 1.0; bool ok_el = true;
+            for (int d = 0; d < dim; d++)
+            {
+               const int side = (k >> d) & 1;            // 0: vertex at xi=0, 1: at xi=1
+               const int el = vnear[d] - side;
+               if (el < 0 || el >= mesh.n[d]) { ok_el = false; break; }
+               double s1 = 0.0;
+               for (int q = 0; q < Q1D; q++)
+               {
+                  const double xi = tab.qx[q];
+                  s1 += tab.qw[q]*pow(side ? xi : 1.0 - xi, (double)sp.ot);
+               }
+               integ *= (mesh.brk[d][el+1] - mesh.brk[d][el])*s1;
+            }
+            if (ok_el) { delta_integral += integ; }
+         }
+      }
       std::vector<int> delta_side((size_t)NE*3, 0); // 0: vertex at xi=0, 1: at xi=1
 
       for (int e = 0; e < NE; e++)
       {
          double lo[3], hi[3]; elem_box(e, lo, hi);
-         int idx[3] = {e % mesh.n[0], (e/mesh.n[0]) % mesh.n[1], e/(mesh.n[0]*mesh.n[1])};
+         int idx[3]; elem_idx(e, idx);
          double xc[3] = {0, 0, 0};
          for (int d = 0; d < dim; d++) { xc[d] = lo[d] + (hi[d] - lo[d])*0.5; }
          gamma[e] = ic.gamma(xc);
@@ -410,10 +458,6 @@ struct Problem
             else if (idx[d] + 1 == vnear[d]) { delta_side[(size_t)e*3 + d] = 1; }
             else { has_vertex = false; }
          }
-         delta_elem[e] = has_vertex;
-
-         double vol = 1.0;
-         for (int d = 0; d < dim; d++) { vol *= (hi[d] - lo[d]); }
 
          for (int lz = 0; lz < LZ; lz++)
             for (int ly = 0; ly < L1D; ly++)
@@ -440,24 +484,6 @@ struct Problem
                   }
                   else { nod_e[li] = ic.e0(x); }
                }
-         if (sp.problem == 1 && has_vertex)
-         {
-            // unit-weight mass integral of the nodal interpolant: sum_q w detJ f(q);
-            // f is a tensor polynomial of degree ot, so Gauss-Legendre(Q1D) is exact.
-            std::vector<double> f1(Q1D);
-            double integ = vol;
-            for (int d = 0; d < dim; d++)
-            {
-               double s = 0.0;
-               for (int q = 0; q < Q1D; q++)
-               {
-                  const double xi = tab.qx[q];
-                  s += tab.qw[q]*pow(delta_side[(size_t)e*3 + d] ? xi : 1.0 - xi, (double)sp.ot);
-               }
-               integ *= s;
-            }
-            delta_integral += integ;
-         }
          nodal_to_bernstein(nod_rho.data(), rho0_gf.data() + (size_t)e*NL);
          nodal_to_bernstein(nod_e.data(), E + (size_t)e*NL);
 

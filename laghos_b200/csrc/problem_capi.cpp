@@ -1,0 +1,112 @@
+// C ABI for the host-side problem setup (include/laghos_b200.h, "Host-side problem setup").
+#include "../../include/laghos_b200.h"
+#include "host/problem.hpp"
+#include "host/partition.hpp"
+#include <string>
+
+namespace lagb { void set_error(const std::string &msg); }
+
+struct lagb_problem { lagb::Problem P; lagb::Partition part; bool partitioned = false; };
+
+extern "C" {
+
+int lagb_problem_create_rect(lagb_problem **out, int dim,
+                             const double *bx, int nbx, const double *by, int nby,
+                             const double *bz, int nbz, int rs, int problem,
+                             int ok, int ot, int oq, double blast_scale, int impose_visc)
+{
+   try
+   {
+      if (dim != 2 && dim != 3) { lagb::set_error("problem_create: dim must be 2 or 3 (PA path, reference laghos.cpp:454-462)"); return LAGB_ERR_INVALID; }
+      if (problem < 0 || problem > 7) { lagb::set_error("Wrong problem specification!"); return LAGB_ERR_INVALID; }
+      std::vector<double> coarse[3];
+      coarse[0].assign(bx, bx + nbx);
+      coarse[1].assign(by, by + nby);
+      if (dim == 3) { coarse[2].assign(bz, bz + nbz); }
+      lagb::RectMesh rm; rm.build(dim, coarse, rs);
+      lagb::ProblemSpec sp;
+      sp.problem = problem; sp.dim = dim; sp.ok = ok; sp.ot = ot; sp.oq = oq;
+      sp.blast_scale = blast_scale; sp.impose_visc = impose_visc != 0;
+      lagb_problem *p = new lagb_problem();
+      p->P.build(sp, rm);
+      *out = p;
+      return LAGB_OK;
+   }
+   catch (const std::exception &e) { lagb::set_error(e.what()); return LAGB_ERR_INVALID; }
+}
+
+int lagb_problem_create(lagb_problem **out, const char *mesh_name, int rs, int problem,
+                        int ok, int ot, int oq, double blast_scale, int impose_visc)
+{
+   std::vector<double> coarse[3]; int dim = 0;
+   if (!mesh_name || !lagb::named_coarse_mesh(mesh_name, dim, coarse))
+   { lagb::set_error(std::string("unknown mesh: ") + (mesh_name ? mesh_name : "(null)")); return LAGB_ERR_INVALID; }
+   return lagb_problem_create_rect(out, dim, coarse[0].data(), (int)coarse[0].size(),
+                                   coarse[1].data(), (int)coarse[1].size(),
+                                   coarse[2].data(), (int)coarse[2].size(), rs, problem, ok, ot, oq,
+                                   blast_scale, impose_visc);
+}
+
+int lagb_problem_create_part(lagb_problem **out, const char *mesh_name, int rs, int problem,
+                             int ok, int ot, int oq, double blast_scale, int impose_visc,
+                             int rank, const int32_t pgrid[3])
+{
+   try
+   {
+      std::vector<double> coarse[3]; int dim = 0;
+      if (!mesh_name || !lagb::named_coarse_mesh(mesh_name, dim, coarse))
+      { lagb::set_error(std::string("unknown mesh: ") + (mesh_name ? mesh_name : "(null)")); return LAGB_ERR_INVALID; }
+      lagb::RectMesh gm; gm.build(dim, coarse, rs);
+      lagb::ProblemSpec sp;
+      sp.problem = problem; sp.dim = dim; sp.ok = ok; sp.ot = ot; sp.oq = oq;
+      sp.blast_scale = blast_scale; sp.impose_visc = impose_visc != 0;
+      lagb_problem *p = new lagb_problem();
+      const int pg[3] = {pgrid[0], pgrid[1], pgrid[2]};
+      p->part.build(dim, gm.n, pg, rank, ok);
+      p->P.build(sp, gm, p->part.lo, p->part.hi);
+      p->partitioned = true;
+      *out = p;
+      return LAGB_OK;
+   }
+   catch (const std::exception &e) { lagb::set_error(e.what()); return LAGB_ERR_INVALID; }
+}
+int lagb_problem_nnbr(const lagb_problem *p) { return p->partitioned ? (int)p->part.nbrs.size() : 0; }
+int lagb_problem_nbr(const lagb_problem *p, int k, int32_t *rank, int32_t *phase, int32_t *n, const int32_t **dofs)
+{
+   if (!p->partitioned || k < 0 || k >= (int)p->part.nbrs.size()) { lagb::set_error("problem_nbr: bad index"); return LAGB_ERR_INVALID; }
+   const auto &nb = p->part.nbrs[k];
+   *rank = nb.rank; *phase = nb.phase; *n = (int32_t)nb.dofs.size(); *dofs = nb.dofs.data();
+   return LAGB_OK;
+}
+const uint8_t *lagb_problem_owner_mask(const lagb_problem *p) { return p->partitioned ? p->part.owner.data() : nullptr; }
+
+void lagb_problem_destroy(lagb_problem *p) { delete p; }
+
+int lagb_problem_get_info(const lagb_problem *p, lagb_problem_info *o)
+{
+   const lagb::Problem &P = p->P;
+   o->dim = P.dim; o->NE = P.NE; o->D1D = P.D1D; o->L1D = P.L1D; o->Q1D = P.Q1D;
+   o->ND = P.ND; o->NL = P.NL; o->NQ = P.NQ;
+   for (int d = 0; d < 3; d++) { o->nelem[d] = P.mesh.n[d]; o->n1[d] = P.N1[d]; o->ness[d] = (d < P.dim) ? (int)P.ess[d].size() : 0; }
+   o->ndofs_h1 = P.ndofs_h1; o->ndofs_l2 = P.ndofs_l2;
+   o->use_visc = P.use_visc; o->use_vort = P.use_vort; o->source = P.source;
+   return LAGB_OK;
+}
+const int32_t *lagb_problem_h1_map(const lagb_problem *p) { return p->P.h1_map.data(); }
+const int32_t *lagb_problem_ess(const lagb_problem *p, int c) { return (c >= 0 && c < p->P.dim) ? p->P.ess[c].data() : nullptr; }
+const double *lagb_problem_S0(const lagb_problem *p) { return p->P.S0.data(); }
+const double *lagb_problem_rho0_gf(const lagb_problem *p) { return p->P.rho0_gf.data(); }
+const double *lagb_problem_rho0_q(const lagb_problem *p) { return p->P.rho0_q.data(); }
+const double *lagb_problem_gamma(const lagb_problem *p) { return p->P.gamma.data(); }
+const double *lagb_problem_qweights(const lagb_problem *p) { return p->P.qweights.data(); }
+const double *lagb_problem_table(const lagb_problem *p, int which)
+{
+   switch (which)
+   {
+      case 0: return p->P.tab.B.data(); case 1: return p->P.tab.G.data(); case 2: return p->P.tab.BL.data();
+      case 3: return p->P.tab.qx.data(); case 4: return p->P.tab.qw.data();
+   }
+   return nullptr;
+}
+
+} // extern "C"

@@ -544,8 +544,8 @@ struct Hydro
       colors.assign(nc, {});
       for (int e = 0; e < P.NE; e++)
       {
-         const int ix = e % P.mesh.n[0], iy = (e/P.mesh.n[0]) % P.mesh.n[1];
-         const int iz = e/(P.mesh.n[0]*P.mesh.n[1]);
+         const int ix = e % P.nloc[0], iy = (e/P.nloc[0]) % P.nloc[1];
+         const int iz = e/(P.nloc[0]*P.nloc[1]);
          colors[(ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2)].push_back(e);
       }
    }

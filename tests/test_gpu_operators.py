@@ -1,0 +1,174 @@
+"""GPU parity tests: every hot-path operator through the C ABI vs the CPU oracle.
+
+Tolerances: M, F, F^T max-norm relative error <= 1e-12 on random and on
+physical inputs; QUpdate stressJinvT <= 1e-11 relative (scaled by the array's max-norm), dt_est
+<= 1e-13; PCG iterates <= 1e-10 relative with iteration counts within +-1.
+"""
+import numpy as np
+import pytest
+
+import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+# (mesh, rs, problem, ok, ot) — 2D and 3D, every order of the BASELINE sweep
+CASES = [
+    ("square01_quad", 2, 0, 2, 1),
+    ("square01_quad", 1, 1, 3, 2),
+    ("square01_quad", 1, 7, 4, 3),
+    ("cube01_hex", 1, 1, 2, 1),
+    ("cube01_hex", 1, 1, 3, 2),
+    ("cube01_hex", 1, 0, 3, 2),
+    ("cube01_hex", 0, 1, 4, 3),
+    ("cube01_hex", 0, 1, 5, 4),
+    ("box01_hex", 0, 3, 3, 2),
+    ("cube01_hex", 0, 1, 1, 0),
+]
+IDS = [f"{m}-rs{rs}-p{p}-Q{ok}Q{ot}" for m, rs, p, ok, ot in CASES]
+
+
+def relerr(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module", params=list(zip(CASES, IDS)), ids=IDS)
+def pair(request, built):
+    from laghos_b200.api import Problem, Context
+    (mesh, rs, problem, ok, ot), _ = request.param
+    P = Problem(mesh, rs, problem, ok, ot)
+    O = pyoracle.Oracle(mesh, rs, problem, ok, ot)
+    ctxs = [Context(P, variant=0), Context(P, variant=1)]
+    yield P, O, ctxs
+    for c in ctxs:
+        c.close()
+
+
+def perturbed_state(P, seed=1234):
+    """x = mesh + 0.1*h*U(-1,1) (keeps detJ>0), v, e random."""
+    rng = np.random.default_rng(seed)
+    S = P.S0.copy()
+    nv = P.h1_vsize
+    n1 = max(P.info.nelem[d] for d in range(P.dim))
+    h = 1.0 / (n1 * (P.D1D - 1)) * 0.5
+    S[:nv] += 0.1 * h * rng.uniform(-1, 1, nv)
+    S[nv:2 * nv] = rng.uniform(-1, 1, nv)
+    S[2 * nv:] = rng.uniform(0.5, 1.5, P.ndofs_l2)
+    return S
+
+
+def test_setup_qdata0(pair):
+    P, O, ctxs = pair
+    for c in ctxs:
+        assert abs(c.h0 - O.h0) <= 1e-14 * O.h0
+        for which in (1, 2, 3, 4):
+            assert relerr(c.qdata(which).cpu().numpy(), O.qdata(which)) < 1e-13
+
+
+def test_vmass_mult(pair):
+    P, O, ctxs = pair
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, P.ndofs_h1)
+    for comp in (-1, 0, P.dim - 1):
+        ref = O.vmass_mult(x, comp)
+        for c in ctxs:
+            y = c.vmass_mult(c.dev(x), comp).cpu().numpy()
+            assert relerr(y, ref) < 1e-12
+            if comp >= 0:
+                assert np.all(y[P.ess(comp)] == 0.0)
+
+
+def test_emass_mult(pair):
+    P, O, ctxs = pair
+    x = np.random.default_rng(8).uniform(-1, 1, P.ndofs_l2)
+    ref = O.emass_mult(x)
+    for c in ctxs:
+        assert relerr(c.emass_mult(c.dev(x)).cpu().numpy(), ref) < 1e-12
+
+
+def test_qupdate_and_force(pair):
+    P, O, ctxs = pair
+    for S in (P.S0.copy(), perturbed_state(P)):
+        dt_ref = O.qupdate(S)
+        sj_ref = O.qdata(0)
+        rng = np.random.default_rng(9)
+        e = rng.uniform(0.5, 1.5, P.ndofs_l2)
+        v = rng.uniform(-1, 1, P.h1_vsize)
+        one = np.ones(P.ndofs_l2)
+        f_ref, f1_ref, ft_ref = O.force_mult(e), O.force_mult(one), O.force_mult_transpose(v)
+        for c in ctxs:
+            dt = c.qupdate(c.dev(S))
+            assert abs(dt - dt_ref) <= 1e-13 * abs(dt_ref), (dt, dt_ref)
+            assert relerr(c.qdata(0).cpu().numpy(), sj_ref) < 1e-11
+            # force operators on the ORACLE's quadrature data (isolates F from Q)
+            c.set_sjit(c.dev(sj_ref))
+            assert relerr(c.force_mult(c.dev(e)).cpu().numpy(), f_ref) < 1e-12
+            assert relerr(c.force_mult(c.dev(one)).cpu().numpy(), f1_ref) < 1e-12
+            assert relerr(c.force_mult_transpose(c.dev(v)).cpu().numpy(), ft_ref) < 1e-12
+
+
+def test_force_adjoint(pair):
+    """<F e, v> == <e, F^T v> (size-independent property)."""
+    P, O, ctxs = pair
+    S = perturbed_state(P, 5)
+    rng = np.random.default_rng(10)
+    e = rng.uniform(-1, 1, P.ndofs_l2)
+    v = rng.uniform(-1, 1, P.h1_vsize)
+    for c in ctxs:
+        c.qupdate(c.dev(S))
+        a = float((c.force_mult(c.dev(e)) * c.dev(v)).sum())
+        b = float((c.dev(e) * c.force_mult_transpose(c.dev(v))).sum())
+        assert abs(a - b) <= 1e-11 * max(abs(a), abs(b), 1e-300)
+
+
+def test_pcg_vmass(pair):
+    P, O, ctxs = pair
+    rng = np.random.default_rng(11)
+    b = rng.uniform(-1, 1, P.h1_vsize)
+    refs = [O.pcg_vmass(comp, b[comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1].copy()) for comp in range(P.dim)]
+    for c in ctxs:
+        for comp in range(P.dim):
+            x, it = c.pcg_vmass(comp, c.dev(b[comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1]))
+            xr, itr = refs[comp]
+            assert abs(it - itr) <= 1, (it, itr)
+            assert relerr(x.cpu().numpy(), xr) < 1e-7   # both stop at rel_tol 1e-8 on the residual
+            assert np.all(x.cpu().numpy()[P.ess(comp)] == 0.0)
+        xa, its = c.pcg_vmass_all(c.dev(b))
+        xa = xa.cpu().numpy()
+        for comp in range(P.dim):
+            xr, itr = refs[comp]
+            assert abs(its[comp] - itr) <= 1
+            assert relerr(xa[comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1], xr) < 1e-7
+
+
+def test_pcg_tight_tolerance(pair):
+    """With -cgt 1e-14 (how the reference runs its cross-backend checks, makefile:199) the
+    solutions agree to ~1e-12."""
+    P, O, ctxs = pair
+    O2 = pyoracle.Oracle(P.args["mesh"], rs=P.args["rs"], problem=P.args["problem"],
+                         ok=P.args["ok"], ot=P.args["ot"], cg_tol=1e-14)
+    b = np.random.default_rng(12).uniform(-1, 1, P.ndofs_h1)
+    xr, _ = O2.pcg_vmass(0, b.copy())
+    for c in ctxs:
+        x, _ = c.pcg_vmass(0, c.dev(b), rel_tol=1e-14)
+        assert relerr(x.cpu().numpy(), xr) < 1e-11
+
+
+def test_cg_emass(pair):
+    P, O, ctxs = pair
+    b = np.random.default_rng(13).uniform(-1, 1, P.ndofs_l2)
+    xr, itr = O.cg_emass(b)
+    for c in ctxs:
+        x, it = c.cg_emass(c.dev(b))
+        assert abs(it - itr) <= 1
+        assert relerr(x.cpu().numpy(), xr) < 1e-6
+
+
+def test_taylor_source_2d(pair):
+    P, O, ctxs = pair
+    if P.dim != 2:
+        pytest.skip("2D only (reference laghos.cpp:638)")
+    S = perturbed_state(P, 3)
+    ref = O.taylor_source(S[:P.h1_vsize].copy())
+    for c in ctxs:
+        assert relerr(c.taylor_source(c.dev(S[:P.h1_vsize])).cpu().numpy(), ref) < 1e-12

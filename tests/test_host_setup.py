@@ -1,0 +1,57 @@
+"""Host logic (no GPU): tables, numbering, initial conditions, element partition."""
+import numpy as np
+import pytest
+
+
+def test_tables_partition_of_unity(built):
+    from laghos_b200.api import Problem
+    for ok, ot in [(1, 0), (2, 1), (3, 2), (4, 3), (5, 4)]:
+        P = Problem("cube01_hex", 0, 1, ok, ot)
+        Q, D, L = P.Q1D, P.D1D, P.L1D
+        B = P.table(0, Q * D).reshape(D, Q)
+        G = P.table(1, Q * D).reshape(D, Q)
+        BL = P.table(2, Q * L).reshape(L, Q)
+        qw = P.table(4, Q)
+        assert np.allclose(B.sum(0), 1.0, atol=1e-14)
+        assert np.allclose(G.sum(0), 0.0, atol=1e-12)
+        assert np.allclose(BL.sum(0), 1.0, atol=1e-14)
+        assert np.all(BL >= 0)
+        assert abs(qw.sum() - 1.0) < 1e-15
+        assert Q == (3 * ok + ot - 1 | 1) // 2 + 1
+
+
+def test_sedov_delta_energy(built):
+    """sum_q w detJ e(q) = E0/2^dim (DeltaCoefficient scaling, laghos.cpp:603-606)."""
+    import pyoracle
+    for mesh, rs in [("square01_quad", 2), ("cube01_hex", 1)]:
+        O = pyoracle.Oracle(mesh, rs, 1, 2, 1)
+        e = O.S0[2 * O.h1_vsize:]
+        # unit-density mass operator applied to e and summed = integral of e (rho0 = 1)
+        assert abs(O.emass_mult(e).sum() - 1.0 / 2 ** O.dim) < 1e-14
+
+
+@pytest.mark.parametrize("pgrid", [(2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2)])
+def test_partition_consistency(built, pgrid):
+    """Boxes tile the mesh, shared lists pair up, each dof has exactly one owner, and ICs agree."""
+    from laghos_b200.api import Problem
+    mesh, rs, ok, ot = "cube01_hex", 1, 2, 1
+    G = Problem(mesh, rs, 1, ok, ot)
+    n = pgrid[0] * pgrid[1] * pgrid[2]
+    parts = [Problem(mesh, rs, 1, ok, ot, rank=r, pgrid=pgrid) for r in range(n)]
+    assert sum(p.NE for p in parts) == G.NE
+    assert sum(int(p.owner_mask.sum()) for p in parts) == G.ndofs_h1
+    x_g = G.S0[:G.h1_vsize].reshape(3, -1)
+    coords = {tuple(np.round(x_g[:, i], 12)): i for i in range(G.ndofs_h1)}
+    for r, p in enumerate(parts):
+        xl = p.S0[:p.h1_vsize].reshape(3, -1)
+        vl = p.S0[p.h1_vsize:2 * p.h1_vsize].reshape(3, -1)
+        vg = G.S0[G.h1_vsize:2 * G.h1_vsize].reshape(3, -1)
+        for i in range(0, p.ndofs_h1, 7):
+            gi = coords[tuple(np.round(xl[:, i], 12))]
+            assert np.array_equal(vl[:, i], vg[:, gi])
+        for (nr, ph, dofs) in p.neighbours():
+            back = [d for (rr, pp, d) in parts[nr].neighbours() if rr == r and pp == ph]
+            assert len(back) == 1 and len(back[0]) == len(dofs)
+            xo = parts[nr].S0[:parts[nr].h1_vsize].reshape(3, -1)
+            assert np.allclose(xl[:, dofs], xo[:, back[0]], atol=0)
+    assert abs(sum(np.abs(p.S0[2 * p.h1_vsize:]).sum() for p in parts) - np.abs(G.S0[2 * G.h1_vsize:]).sum()) < 1e-12
