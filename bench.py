@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's figure of merit on BASELINE.json's workload.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU -pa algorithm (oracle port)
+
+A "step" is one RK4 time step of the Laghos hot path (4 x [QUpdate, Force, dim x PCG(mass),
+Force^T, CG(L2 mass)] + the post-step dt estimate) through the restated driver loop
+(lagb_laghos_run = reference laghos.cpp:742-778) on the 3D Sedov problem, Q3/Q2.
+
+N = 1 : BASELINE config[1]  cube01_hex -p 1 -rs 5 -ok 3 -ot 2 -pa  (64^3 elements).
+N > 1 : weak scaling, one 64^3-element block per GPU (2x1x1, 2x2x1, 2x2x2 blocks; N = 8 is
+        BASELINE config[3], cube01_hex -rs 6), launched by torchrun, NCCL for the CG dots,
+        the shared-dof sums and min(dt).
+
+metric : "Major kernels total rate" (reference laghos_solver.cpp:721-727): Mdof x steps / s =
+         work / (T_cgH1 + T_force + T_qdata), work = 1e-6 (H1 dofs x CG its + (H1+L2) dofs x stages +
+         quad points x updates), timers = CUDA events on the context stream, max over ranks.
+value  : that rate with the state resident in HBM.
+e2e    : work / device time of the WHOLE timed loop (incl. RK vector ops, L2 CG, dt read-back)
+         of a second run in which the state S lives in pinned host memory and is copied H2D
+         before and D2H after every step through the C ABI.
+roofline: the H1 mass-apply kernel (mass3d, 3 components per launch inside the batched PCG),
+         average CUDA-event duration over every launch of the timed region vs algorithmic bytes
+         8 (NQ NE + 2*3 ndofs)  (SURVEY.md 8d).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mdof x steps / s (major kernels total rate), 3D Sedov Q3/Q2 -pa"
+UNIT = "Mdof*steps/s"
+PGRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def workload(n_gpus, rs):
+    """mesh name + rs such that every GPU owns a (2^rs)^3-element block of edge-2^-(rs+1) hexes."""
+    pg = PGRIDS[n_gpus]
+    if n_gpus == 1:
+        return dict(mesh="cube01_hex", rs=rs), pg, f"cube01_hex -p 1 -rs {rs} -ok 3 -ot 2 -pa"
+    mesh = "cube01_hex" if n_gpus == 8 else f"hexbox_{pg[0]}x{pg[1]}x{pg[2]}"
+    return dict(mesh=mesh, rs=rs + 1), pg, f"{mesh} -p 1 -rs {rs + 1} -ok 3 -ot 2 -pa, {pg[0]}x{pg[1]}x{pg[2]} blocks"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_oracle_run(threads, budget_s, steps, warmup):
+    """The reference's CPU -pa algorithm (oracle port, element-parallel over `threads` host threads,
+    the stand-in for `mpirun -np <cores> laghos`) on a bounded sample of the same workload:
+    same problem / orders, smaller -rs.  Returns (rate, sample description, work, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    kw = dict(mesh="cube01_hex", problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, nthreads=threads)
+    rs, best = 2, None
+    t_total0 = time.time()
+    while rs <= 5:
+        t0 = time.time()
+        r = pyoracle.run(rs=rs, max_tsteps=steps + warmup, **kw)
+        el = time.time() - t0
+        best = (rs, r, el)
+        # next level costs ~8x; stop when it would not fit the budget
+        if (time.time() - t_total0) + 8.5 * el > budget_s:
+            break
+        rs += 1
+    rs, r, el = best
+    T = r["t_cgH1"] + r["t_force"] + r["t_qdata"]
+    sample = (f"oracle port (reference serial -pa algorithm, {threads} element-parallel host threads), "
+              f"cube01_hex -p 1 -rs {rs} -ok 3 -ot 2, {r['steps']} RK4 steps from t=0, {el:.1f} s wall")
+    return r["fom"][0], sample, T, el, rs, r
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the
+    reference binary cannot be built here: MFEM/MPI/hypre absent)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    fom, sample, T, el, rs, r = cpu_oracle_run(threads, budget_s=150.0, steps=args.steps, warmup=0)
+    steps = max(r["steps"], 1)
+    work = fom * T
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fom, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 0, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3D Sedov cube01_hex -p 1 -ok 3 -ot 2 -pa, bounded CPU sample -rs {rs} "
+                               f"(GPU arm runs -rs {args.rs}); rates are per dof so they compare",
+                   "cg_tol": 1e-8, "ode": "RK4"},
+        "cpu_baseline": {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": work / el, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rs", type=int, default=5, help="refinements per GPU block (5 = 64^3 elements, BASELINE)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variant", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.gpus not in PGRIDS:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+
+    import torch
+    import torch.distributed as dist
+    from laghos_b200.api import run
+    from laghos_b200 import load_library
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: laghos_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    lib = load_library()
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes
+            buf = ctypes.create_string_buffer(128)
+            assert lib.lagb_nccl_unique_id(buf) == 0, lib.lagb_last_error()
+            idt = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        idt = idt.cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    wl, pg, wl_name = workload(args.gpus, args.rs)
+    kw = dict(problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, max_tsteps=args.warmup + args.steps,
+              warmup_steps=args.warmup, kernel_variant=args.variant, device=local, rank=rank, nranks=world,
+              pgrid=pg, nccl_id=nccl_id, **wl)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    r = run(profile_mass=True, **kw)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        r2 = run(e2e_host_state=True, **kw)
+        barrier()
+        t2 = torch.tensor([r2["device_seconds"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([float(r2["h2d_bytes_per_step"]), float(r2["d2h_bytes_per_step"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+        e2e = {"value": r2["work_mdof"] / float(t2.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
+               "ms_per_step": 1e3 * float(t2.item()) / args.steps}
+    # whole-loop device time, max over ranks (FOM timers are already max-reduced inside the run)
+    t = torch.tensor([r["device_seconds"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    loop_s = float(t.item())
+
+    if rank == 0:
+        timed_steps = r["steps"] - args.warmup
+        peak, peak_src = peaks()
+        NE_loc, NQ, nd_loc = (2 ** args.rs) ** 3, 216, (3 * 2 ** args.rs + 1) ** 3
+        ncomp = int(r["mass_kernel_ncomp"])
+        alg_bytes = 8.0 * (NQ * NE_loc + 2 * ncomp * nd_loc)
+        nl = max(int(r["mass_kernel_launches"]), 1)
+        avg_s = r["mass_kernel_seconds"] / nl
+        achieved = alg_bytes / avg_s / 1e9 if avg_s > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "mass3d_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        T_major = r["fom"][4]
+        line = {
+            "metric": METRIC, "value": r["fom"][0], "unit": UNIT, "n_gpus": args.gpus, "steps": timed_steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * loop_s / max(timed_steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "elements_per_gpu": NE_loc, "h1_dofs_global": r["ndofs_h1_global"],
+                       "l2_dofs_global": r["ndofs_l2_global"], "ode": "RK4", "cg_tol": 1e-8, "batched_pcg": True,
+                       "l2_flush": "inputs larger than L2 (quadrature data 4.5 GB per operator pass)",
+                       "parallelism": f"element blocks {pg[0]}x{pg[1]}x{pg[2]}"},
+            "phases": {"cgH1_Mdof_its_per_s": r["fom"][1], "force_Mdof_steps_per_s": r["fom"][2],
+                       "qdata_Mquad_steps_per_s": r["fom"][3], "t_cgH1_s": r["t_cgH1"], "t_force_s": r["t_force"],
+                       "t_qdata_s": r["t_qdata"], "t_cgL2_s": r["t_cgL2"], "t_major_s": T_major,
+                       "H1_cg_iterations": r["H1iter"], "loop_device_s": loop_s},
+            "roofline": {"kernel": f"mass3d<4,6> NC={ncomp} (H1 mass PA apply inside the batched PCG)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e6 * avg_s, "launches": nl,
+                         "share_of_major_time": r["mass_kernel_seconds"] / T_major if T_major > 0 else None},
+            "e2e": e2e, "gpu_launches": int(r["kernel_launches"]), "clocks": clocks,
+            "e_norm": r["e_norm"],
+        }
+        if not args.no_cpu and args.gpus == 1:
+            threads = os.cpu_count() or 1
+            fom, sample, _, _, _, _ = cpu_oracle_run(threads, budget_s=25.0, steps=2, warmup=0)
+            line["cpu_baseline"] = {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -231,6 +231,13 @@ typedef struct lagb_timing
 } lagb_timing;
 int lagb_timing_get(lagb_ctx *ctx, lagb_timing *out);
 int lagb_timing_reset(lagb_ctx *ctx);
+/* Measurement aids (bench.py): a CUDA-event stopwatch on the context stream, and per-launch
+ * CUDA-event timing of the H1 mass-apply kernel inside the PCG (the dominant kernel; its
+ * average duration is the denominator of the roofline figure).  lagb_timing_reset clears both. */
+int lagb_stopwatch_start(lagb_ctx *ctx);
+int lagb_stopwatch_stop(lagb_ctx *ctx, double *seconds);   /* synchronises */
+int lagb_profile_mass(lagb_ctx *ctx, int enable);
+int lagb_profile_mass_get(lagb_ctx *ctx, double *seconds, int64_t *launches);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ class RunOptions(C.Structure):
                 ("batched_pcg", C.c_int), ("kernel_variant", C.c_int), ("device", C.c_int),
                 ("verbose", C.c_int), ("vis_steps", C.c_int), ("e2e_host_state", C.c_int),
                 ("warmup_steps", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("pgrid", C.c_int * 3),
-                ("nccl_id", C.c_void_p)]
+                ("nccl_id", C.c_void_p), ("profile_mass", C.c_int)]
 
 
 class RunResult(C.Structure):
@@ -51,7 +51,9 @@ class RunResult(C.Structure):
                 ("wall_seconds", C.c_double), ("device_seconds", C.c_double),
                 ("h2d_bytes_per_step", C.c_int64), ("d2h_bytes_per_step", C.c_int64),
                 ("kernel_launches", C.c_int64), ("n_hist", C.c_int),
-                ("ndofs_h1_global", C.c_int64), ("ndofs_l2_global", C.c_int64), ("ne_global", C.c_int64)]
+                ("ndofs_h1_global", C.c_int64), ("ndofs_l2_global", C.c_int64), ("ne_global", C.c_int64),
+                ("mass_kernel_seconds", C.c_double), ("mass_kernel_launches", C.c_int64),
+                ("mass_kernel_ncomp", C.c_int64), ("work_mdof", C.c_double)]
 
 
 # every symbol include/laghos_b200.h declares (tests/test_abi_symbols.py checks the
@@ -66,7 +68,8 @@ lagb_qupdate_async lagb_dt_est_read lagb_pcg_vmass lagb_pcg_vmass_all lagb_cg_em
 lagb_qdata_ptr lagb_qdata_h0 lagb_qdata_set_h0 lagb_dev_malloc lagb_dev_free lagb_memcpy_h2d
 lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_host_alloc_pinned lagb_host_free_pinned lagb_vec_fill
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
-lagb_timing_get lagb_timing_reset""".split()
+lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
+lagb_profile_mass lagb_profile_mass_get""".split()
 
 
 def load_library():
@@ -132,6 +135,10 @@ def load_library():
     lib.lagb_allreduce_host.argtypes = [vp, c_double_p, i32, i32]
     lib.lagb_timing_get.argtypes = [vp, C.POINTER(Timing)]
     lib.lagb_timing_reset.argtypes = [vp]
+    lib.lagb_stopwatch_start.argtypes = [vp]
+    lib.lagb_stopwatch_stop.argtypes = [vp, c_double_p]
+    lib.lagb_profile_mass.argtypes = [vp, i32]
+    lib.lagb_profile_mass_get.argtypes = [vp, c_double_p, C.POINTER(i64)]
     lib.lagb_laghos_run.argtypes = [C.POINTER(RunOptions), C.POINTER(RunResult), c_double_p, i32, c_double_p]
     lib.lagb_run_options_default.argtypes = [C.POINTER(RunOptions)]
     _lib = lib

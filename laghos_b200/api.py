@@ -264,7 +264,8 @@ class Context:
 def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None, impose_visc=False,
         ode_solver_type=4, t_final=0.6, max_tsteps=-1, cfl=0.5, cg_tol=1e-8, cg_max_iter=300,
         batched_pcg=True, kernel_variant=0, device=0, verbose=False, vis_steps=5, e2e_host_state=False,
-        warmup_steps=0, rank=0, nranks=1, pgrid=(1, 1, 1), nccl_id=None, hist_cap=0, want_state=False):
+        warmup_steps=0, rank=0, nranks=1, pgrid=(1, 1, 1), nccl_id=None, hist_cap=0, want_state=False,
+        profile_mass=False):
     """The reference driver's run (laghos.cpp main) through the C++ shim: lagb_laghos_run."""
     lib = load_library()
     dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
@@ -281,6 +282,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     o.batched_pcg, o.kernel_variant, o.device = int(batched_pcg), kernel_variant, device
     o.verbose, o.vis_steps, o.e2e_host_state, o.warmup_steps = int(verbose), vis_steps, int(e2e_host_state), warmup_steps
     o.rank, o.nranks = rank, nranks
+    o.profile_mass = int(profile_mass)
     for d in range(3):
         o.pgrid[d] = pgrid[d]
     idbuf = None
@@ -301,7 +303,9 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     out = dict(steps=r.steps, ti_last=r.ti_last, stages=r.stages, t=r.t, dt=r.dt, e_norm=r.e_norm,
                fom=list(r.fom), t_cgH1=r.timing.t_cgH1, t_cgL2=r.timing.t_cgL2, t_force=r.timing.t_force,
                t_qdata=r.timing.t_qdata, H1iter=r.timing.H1iter, L2iter=r.timing.L2iter,
-               quad_tstep=r.timing.quad_tstep, wall_seconds=r.wall_seconds,
+               quad_tstep=r.timing.quad_tstep, wall_seconds=r.wall_seconds, device_seconds=r.device_seconds,
+               mass_kernel_seconds=r.mass_kernel_seconds, mass_kernel_launches=r.mass_kernel_launches,
+               mass_kernel_ncomp=r.mass_kernel_ncomp, work_mdof=r.work_mdof,
                h2d_bytes_per_step=r.h2d_bytes_per_step, d2h_bytes_per_step=r.d2h_bytes_per_step,
                kernel_launches=r.kernel_launches, ndofs_h1_global=r.ndofs_h1_global,
                ndofs_l2_global=r.ndofs_l2_global, ne_global=r.ne_global,

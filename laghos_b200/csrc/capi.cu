@@ -27,16 +27,21 @@ static cudaEvent_t timer_event(Ctx &c)
 }
 static int timer_resolve(Ctx &c)
 {
-   for (int w = 0; w < 4; w++)
+   for (int w = 0; w < Timer::NT; w++)
    {
-      for (auto &p : c.timer.pending[w])
+      auto &pend = c.timer.pending[w];
+      // an interval whose end event is not recorded yet (timers nest) stays pending
+      const bool keep_last = !pend.empty() && c.timer.open[w];
+      const size_t n = pend.size() - (keep_last ? 1 : 0);
+      for (size_t i = 0; i < n; i++)
       {
+         auto &p = pend[i];
          LAGB_CUDA(cudaEventSynchronize(p.second));
          float ms = 0.f; LAGB_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
          c.timer.acc[w] += 1e-3*ms;
          c.timer.pool.push_back(p.first); c.timer.pool.push_back(p.second);
       }
-      c.timer.pending[w].clear();
+      pend.erase(pend.begin(), pend.begin() + n);
    }
    return LAGB_OK;
 }
@@ -45,11 +50,13 @@ int timer_begin(Ctx &c, int w)
    cudaEvent_t a = timer_event(c), b = timer_event(c);
    LAGB_CUDA(cudaEventRecord(a, c.stream));
    c.timer.pending[w].push_back({a, b});
+   c.timer.open[w] = true;
    return LAGB_OK;
 }
 int timer_end(Ctx &c, int w)
 {
    LAGB_CUDA(cudaEventRecord(c.timer.pending[w].back().second, c.stream));
+   c.timer.open[w] = false;
    if (c.timer.pending[w].size() > 4096) { return timer_resolve(c); }
    return LAGB_OK;
 }
@@ -211,8 +218,10 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    {
       den_blocks = 0;
       if (l2) { return ks.mass_l2(c, v, z); }
+      if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
       int rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass);
       if (rc) { return rc; }
+      if (c.profile_mass) { int rt = timer_end(c, 4); if (rt) { return rt; } c.mass_launches++; }
       if (want_den && ks.tuned_mass) { den_blocks = c.dt_nblocks; }
       return halo_sum(c, z, NC);
    };
@@ -368,7 +377,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
    if (c.h_state) { cudaFreeHost(c.h_state); }
    if (c.h_scal) { cudaFreeHost(c.h_scal); }
-   for (int w = 0; w < 4; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
+   for (int w = 0; w < Timer::NT; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
    for (auto e : c.timer.pool) { cudaEventDestroy(e); }
    if (c.nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c.nccl_comm); }
    delete h;
@@ -700,8 +709,34 @@ int lagb_timing_reset(lagb_ctx *h)
 {
    Ctx &c = h->c;
    int rc = timer_resolve(c); if (rc) { return rc; }
-   for (int w = 0; w < 4; w++) { c.timer.acc[w] = 0.0; }
-   c.H1iter = c.L2iter = c.quad_tstep = 0;
+   for (int w = 0; w < Timer::NT; w++) { c.timer.acc[w] = 0.0; }
+   c.H1iter = c.L2iter = c.quad_tstep = 0; c.mass_launches = 0;
+   return LAGB_OK;
+}
+
+int lagb_profile_mass(lagb_ctx *h, int enable) { h->c.profile_mass = enable != 0; return LAGB_OK; }
+int lagb_profile_mass_get(lagb_ctx *h, double *seconds, int64_t *launches)
+{
+   Ctx &c = h->c;
+   int rc = timer_resolve(c); if (rc) { return rc; }
+   if (seconds) { *seconds = c.timer.acc[4]; }
+   if (launches) { *launches = c.mass_launches; }
+   return LAGB_OK;
+}
+int lagb_stopwatch_start(lagb_ctx *h)
+{
+   Ctx &c = h->c;
+   int rc = timer_resolve(c); if (rc) { return rc; }
+   c.timer.acc[5] = 0.0;
+   return timer_begin(c, 5);
+}
+int lagb_stopwatch_stop(lagb_ctx *h, double *seconds)
+{
+   Ctx &c = h->c;
+   if (c.timer.pending[5].empty()) { set_error("stopwatch_stop without start"); return LAGB_ERR_STATE; }
+   int rc = timer_end(c, 5); if (rc) { return rc; }
+   rc = timer_resolve(c); if (rc) { return rc; }
+   if (seconds) { *seconds = c.timer.acc[5]; }
    return LAGB_OK;
 }
 

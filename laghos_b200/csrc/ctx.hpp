@@ -34,9 +34,12 @@ struct KernelSet
 
 struct Timer
 {
-   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[4];
+   static constexpr int NT = 6;
+   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[NT];
    std::vector<cudaEvent_t> pool;
-   double acc[4] = {0, 0, 0, 0}; // cgH1, cgL2, force, qdata (seconds)
+   // cgH1, cgL2, force, qdata, [4] = H1 mass-apply kernel alone (lagb_profile_mass), [5] = stopwatch
+   double acc[NT] = {0, 0, 0, 0, 0, 0};
+   bool open[NT] = {false, false, false, false, false, false};   // newest interval has no end event yet
 };
 
 struct NcclApi;
@@ -70,6 +73,7 @@ struct Ctx
    int predicted_iters = 0;
    // timing
    Timer timer; int64_t H1iter = 0, L2iter = 0, quad_tstep = 0;
+   bool profile_mass = false; int64_t mass_launches = 0;
    // multi-rank
    int rank = 0, nranks = 1; void *nccl_comm = nullptr;
    struct Nbr { int rank, phase, n; int *d_idx; double *d_send, *d_recv; };

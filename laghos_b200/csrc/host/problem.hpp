@@ -83,6 +83,17 @@ inline bool named_coarse_mesh(const std::string &name, int &dim,
    { dim = 2; coarse[0] = {-.5, 0, .5}; coarse[1] = {-.5, 0, .5}; return true; }
    if (name == "rt2D")
    { dim = 2; coarse[0] = {0, .5}; coarse[1] = {-1, -.5, 0, .5, 1}; return true; }
+   // weak-scaling family (not a reference mesh): hexbox_PxQxR = P x Q x R coarse hexes of
+   // edge 0.5 starting at the origin, so hexbox_2x2x2 == cube01_hex and every member has
+   // the same element size at equal -rs (bench.py --gpus 2 / 4).
+   int p = 0, q = 0, r = 0;
+   if (sscanf(name.c_str(), "hexbox_%dx%dx%d", &p, &q, &r) == 3 && p > 0 && q > 0 && r > 0 && p <= 64 && q <= 64 && r <= 64)
+   {
+      dim = 3;
+      const int n[3] = {p, q, r};
+      for (int d = 0; d < 3; d++) { for (int i = 0; i <= n[d]; i++) { coarse[d].push_back(0.5*i); } }
+      return true;
+   }
    return false;
 }
 

@@ -371,6 +371,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
       double t = 0.0, dt = hydro.GetTimeStepEstimate(S), t_old;
       bool last_step = false;
       int steps = 0, timed_from_step = 0;
+      bool sw_started = false;
       Vector e_gf; e_gf.MakeRef(S, 2*NV, P.ndofs_l2);
       auto e_norm = [&]()
       {
@@ -380,7 +381,13 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
       };
       auto t_wall0 = std::chrono::steady_clock::now();
       int64_t launches0 = lagb_kernel_launch_count();
-      if (opt->warmup_steps <= 0) { LAGHOS_CHECK(lagb_timing_reset(ctx)); LAGHOS_CHECK(lagb_ctx_sync(ctx)); t_wall0 = std::chrono::steady_clock::now(); }
+      LAGHOS_CHECK(lagb_profile_mass(ctx, opt->profile_mass));
+      if (opt->warmup_steps <= 0)
+      {
+         LAGHOS_CHECK(lagb_timing_reset(ctx)); LAGHOS_CHECK(lagb_ctx_sync(ctx));
+         t_wall0 = std::chrono::steady_clock::now();
+         LAGHOS_CHECK(lagb_stopwatch_start(ctx)); sw_started = true;
+      }
       int n_hist = 0, ti = 1;
       for (; !last_step; ti++)
       {
@@ -421,11 +428,15 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          {
             LAGHOS_CHECK(lagb_timing_reset(ctx)); LAGHOS_CHECK(lagb_ctx_sync(ctx));
             t_wall0 = std::chrono::steady_clock::now(); launches0 = lagb_kernel_launch_count();
+            LAGHOS_CHECK(lagb_stopwatch_start(ctx)); sw_started = true;
             timed_from_step = steps;
          }
       }
-      LAGHOS_CHECK(lagb_ctx_sync(ctx));
+      if (!sw_started) { LAGHOS_CHECK(lagb_stopwatch_start(ctx)); }
+      LAGHOS_CHECK(lagb_stopwatch_stop(ctx, &res->device_seconds));
       const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wall0).count();
+      LAGHOS_CHECK(lagb_profile_mass_get(ctx, &res->mass_kernel_seconds, &res->mass_kernel_launches));
+      res->mass_kernel_ncomp = opt->batched_pcg ? P.dim : 1;
       res->steps = steps; res->t = t; res->dt = dt; res->stages = stages; res->n_hist = n_hist;
       res->wall_seconds = wall;
       res->kernel_launches = lagb_kernel_launch_count() - launches0;
@@ -457,6 +468,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          res->fom[3] = 1e-6*sizes[3]*P.NQ/T3;
          res->fom[0] = (res->fom[1]*T0 + res->fom[2]*T2 + res->fom[3]*T3)/T4;
          res->fom[4] = T4;
+         res->work_mdof = 1e-6*(H1GTVSize*H1iter + timed_steps*(H1GTVSize + L2GTVSize) + sizes[3]*P.NQ);
       }
       if (S_out) { std::vector<double> tmp; S.HostRead(tmp); memcpy(S_out, tmp.data(), sizeof(double)*N); }
       if (opt->verbose && opt->rank == 0)

@@ -251,6 +251,7 @@ typedef struct lagb_run_options
    int rank, nranks;
    int pgrid[3];
    const unsigned char *nccl_id; // 128 bytes from lagb_nccl_unique_id (rank 0), broadcast by the launcher
+   int profile_mass;        // 1: CUDA-event timing of every H1 mass-apply launch (bench roofline)
 } lagb_run_options;
 
 typedef struct lagb_run_result
@@ -265,6 +266,10 @@ typedef struct lagb_run_result
    int64_t kernel_launches;
    int n_hist;
    int64_t ndofs_h1_global, ndofs_l2_global, ne_global;
+   double mass_kernel_seconds;      // profile_mass: summed duration and count of the H1 mass-apply launches
+   int64_t mass_kernel_launches;
+   int64_t mass_kernel_ncomp;       // components per launch (3 = batched PCG)
+   double work_mdof;                // numerator of the FOM: 1e-6 * (H1 dofs x CG its + (H1+L2) dofs x stages + quad points x updates)
 } lagb_run_result;
 
 // hist: [2*hist_cap] (ti, |e|) pairs after every accepted step; S_out (optional): final state on the host
