@@ -110,11 +110,12 @@ def cpu_oracle_run(threads, budget_s, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     kw = dict(mesh="cube01_hex", problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, nthreads=threads)
-    rs, best = 2, None
+    rs, best = 3, None
     t_total0 = time.time()
     while rs <= 5:
         t0 = time.time()
-        r = pyoracle.run(rs=rs, max_tsteps=steps + warmup, **kw)
+        kw["nthreads"] = max(1, min(threads, (2 ** (rs + 1)) ** 3 // 64))
+        r = pyoracle.run(rs=rs, max_tsteps=steps + warmup - 1, **kw)
         el = time.time() - t0
         best = (rs, r, el)
         # next level costs ~8x; stop when it would not fit the budget
@@ -123,9 +124,10 @@ def cpu_oracle_run(threads, budget_s, steps, warmup):
         rs += 1
     rs, r, el = best
     T = r["t_cgH1"] + r["t_force"] + r["t_qdata"]
+    threads = kw["nthreads"]
     sample = (f"oracle port (reference serial -pa algorithm, {threads} element-parallel host threads), "
               f"cube01_hex -p 1 -rs {rs} -ok 3 -ot 2, {r['steps']} RK4 steps from t=0, {el:.1f} s wall")
-    return r["fom"][0], sample, T, el, rs, r
+    return r["fom"][0], sample, T, el, rs, r, threads
 
 
 def run_reference(args, rank, world):
@@ -134,7 +136,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    fom, sample, T, el, rs, r = cpu_oracle_run(threads, budget_s=150.0, steps=args.steps, warmup=0)
+    fom, sample, T, el, rs, r, threads = cpu_oracle_run(threads, budget_s=150.0, steps=args.steps, warmup=0)
     steps = max(r["steps"], 1)
     work = fom * T
     line = {
@@ -196,7 +198,7 @@ def main():
         nccl_id = bytes(idt.cpu().tolist())
 
     wl, pg, wl_name = workload(args.gpus, args.rs)
-    kw = dict(problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, max_tsteps=args.warmup + args.steps,
+    kw = dict(problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, max_tsteps=args.warmup + args.steps - 1,   # the reference loop runs max_tsteps + 1 steps (laghos.cpp:749-760)
               warmup_steps=args.warmup, kernel_variant=args.variant, device=local, rank=rank, nranks=world,
               pgrid=pg, nccl_id=nccl_id, **wl)
 
@@ -235,7 +237,8 @@ def main():
     if rank == 0:
         timed_steps = r["steps"] - args.warmup
         peak, peak_src = peaks()
-        NE_loc, NQ, nd_loc = (2 ** args.rs) ** 3, 216, (3 * 2 ** args.rs + 1) ** 3
+        n1 = 2 ** (args.rs + 1)          # elements per axis of one GPU's block (cube01_hex: 2 coarse cells x 2^rs)
+        NE_loc, NQ, nd_loc = n1 ** 3, 216, (3 * n1 + 1) ** 3
         ncomp = int(r["mass_kernel_ncomp"])
         alg_bytes = 8.0 * (NQ * NE_loc + 2 * ncomp * nd_loc)
         nl = max(int(r["mass_kernel_launches"]), 1)
@@ -268,7 +271,7 @@ def main():
         }
         if not args.no_cpu and args.gpus == 1:
             threads = os.cpu_count() or 1
-            fom, sample, _, _, _, _ = cpu_oracle_run(threads, budget_s=25.0, steps=2, warmup=0)
+            fom, sample, _, _, _, _, threads = cpu_oracle_run(threads, budget_s=25.0, steps=2, warmup=0)
             line["cpu_baseline"] = {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -130,6 +130,10 @@ int lagb_setup_qdata0(lagb_ctx *ctx, const double *d_x0, const double *d_rho0_gf
 /* MassPAOperator::Mult (laghos_assembly.cpp:117-121): y = M x on the scalar H1
  * space, then y[ess(comp)] = 0.  comp = -1: MultFull (laghos_assembly.hpp:128). */
 int lagb_vmass_mult(lagb_ctx *ctx, int comp, const double *d_x, double *d_y);
+/* the same for all `dim` components of an H1 vector at once (byNODES), no essential-dof
+ * zeroing: y_c = M x_c.  One pass over the quadrature data for all components (the kernel
+ * the batched PCG runs every iteration). */
+int lagb_vmass_mult_all(lagb_ctx *ctx, const double *d_x, double *d_y);
 /* OperatorJacobiSmoother diagonal (laghos_solver.cpp:268-270): d_diag[ndofs_h1] */
 int lagb_vmass_diag(lagb_ctx *ctx, double *d_diag);
 /* MassPAOperator(L2)::Mult (laghos_solver.cpp:179): block-diagonal Bernstein mass */
@@ -238,6 +242,8 @@ int lagb_stopwatch_start(lagb_ctx *ctx);
 int lagb_stopwatch_stop(lagb_ctx *ctx, double *seconds);   /* synchronises */
 int lagb_profile_mass(lagb_ctx *ctx, int enable);
 int lagb_profile_mass_get(lagb_ctx *ctx, double *seconds, int64_t *launches);
+/* kernel tuning knobs (tools/microbench.py): key 0 = launch variant of the 3-component mass apply */
+int lagb_tune_set(lagb_ctx *ctx, int key, int value);
 
 #ifdef __cplusplus
 }

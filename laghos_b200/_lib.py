@@ -69,7 +69,7 @@ lagb_qdata_ptr lagb_qdata_h0 lagb_qdata_set_h0 lagb_dev_malloc lagb_dev_free lag
 lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_host_alloc_pinned lagb_host_free_pinned lagb_vec_fill
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
-lagb_profile_mass lagb_profile_mass_get""".split()
+lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set""".split()
 
 
 def load_library():
@@ -111,6 +111,8 @@ def load_library():
     lib.lagb_setup_qdata0.argtypes = [vp, vp, vp, vp, i64, c_double_p]
     lib.lagb_vmass_mult.argtypes = [vp, i32, vp, vp]
     lib.lagb_vmass_diag.argtypes = [vp, vp]
+    lib.lagb_vmass_mult_all.argtypes = [vp, vp, vp]
+    lib.lagb_tune_set.argtypes = [vp, i32, i32]
     lib.lagb_emass_mult.argtypes = [vp, vp, vp]
     lib.lagb_force_mult.argtypes = [vp, vp, vp]
     lib.lagb_force_mult_transpose.argtypes = [vp, vp, vp]

@@ -178,6 +178,14 @@ class Context:
         _check(self.lib, self.lib.lagb_vmass_mult(self.h, comp, self._p(x), self._p(y)))
         return y
 
+    def vmass_mult_all(self, x, y=None):
+        y = self.empty(self.P.h1_vsize) if y is None else y
+        _check(self.lib, self.lib.lagb_vmass_mult_all(self.h, self._p(x), self._p(y)))
+        return y
+
+    def tune(self, key, value):
+        _check(self.lib, self.lib.lagb_tune_set(self.h, key, value))
+
     def vmass_diag(self):
         y = self.empty(self.P.ndofs_h1)
         _check(self.lib, self.lib.lagb_vmass_diag(self.h, self._p(y)))

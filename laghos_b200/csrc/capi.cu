@@ -445,6 +445,22 @@ int lagb_vmass_mult(lagb_ctx *h, int comp, const double *d_x, double *d_y)
    return LAGB_OK;
 }
 
+int lagb_vmass_mult_all(lagb_ctx *h, const double *d_x, double *d_y)
+{
+   Ctx &c = h->c;
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   LAGB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double)*c.ndofs*c.dim, c.stream));
+   int rc = ks.mass_h1(c, c.dim, d_x, d_y, false); if (rc) { return rc; }
+   return halo_sum(c, d_y, c.dim);
+}
+
+int lagb_tune_set(lagb_ctx *h, int key, int value)
+{
+   if (key < 0 || key >= 8) { set_error("tune_set: bad key"); return LAGB_ERR_INVALID; }
+   h->c.tune[key] = value;
+   return LAGB_OK;
+}
+
 int lagb_vmass_diag(lagb_ctx *h, double *d_diag)
 {
    Ctx &c = h->c;

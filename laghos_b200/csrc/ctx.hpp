@@ -70,6 +70,7 @@ struct Ctx
    double h0 = 0.0;
    bool setup_done = false;
    int dt_nblocks = 0;
+   int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // lagb_tune_set: [0] mass3d NC=3 variant
    int predicted_iters = 0;
    // timing
    Timer timer; int64_t H1iter = 0, L2iter = 0, quad_tstep = 0;

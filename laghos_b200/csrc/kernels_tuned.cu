@@ -1,27 +1,32 @@
 // Launchers for the tuned 3D kernels (sm_100a).
 #include "ctx.hpp"
 #include "device/mass3d.cuh"
+#include "device/staged3d.cuh"
 
 namespace lagb {
 
-template<int D1D, int Q1D, int NB1, int NB3>
+template<typename K>
+static int set_smem(K kern, size_t bytes)
+{
+   LAGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+   return LAGB_OK;
+}
+
+// <D1D, Q1D, NB1, MINB1, NB3, MINB3, NTQ, NTF>: elements per CTA and minimum resident CTAs
+// for the 1- and 3-component mass apply, threads per element of QUpdate, threads of Force.
+template<int D1D, int Q1D, int NB1, int MINB1, int NB3, int MINB3, int NTQ, int NTF>
 struct TunedLaunch3D
 {
    using Tab = DevTables<D1D,Q1D>;
    static const Tab &tab(Ctx &c) { return *reinterpret_cast<const Tab*>(c.tab_blob.data()); }
 
-   template<int NC, bool WITH_DEN>
-   static int mass_launch(Ctx &c, const double *x, double *y)
+   template<int NC, bool WITH_DEN, int NB, int MINB>
+   static int mass_launch_v(Ctx &c, const double *x, double *y)
    {
-      constexpr int NB = (NC == 1) ? NB1 : NB3;
       using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
-      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN>;
+      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB>;
       static bool attr_set = false;
-      if (!attr_set)
-      {
-         LAGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-         attr_set = true;
-      }
+      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
       const int grid = (c.NE + NB - 1)/NB;
       if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
       kern<<<grid, Cfg::T, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part);
@@ -29,30 +34,95 @@ struct TunedLaunch3D
       if (WITH_DEN) { c.dt_nblocks = grid; }
       return LAGB_OK;
    }
+   template<int NC, bool WITH_DEN>
+   static int mass_launch(Ctx &c, const double *x, double *y)
+   {
+      if (NC == 3 && D1D == 4)   // tuning variants of the dominant kernel (lagb_tune_set key 0)
+      {
+         switch (c.tune[0])
+         {
+            case 1: return mass_launch_v<NC,WITH_DEN,16,2>(c, x, y);
+            case 2: return mass_launch_v<NC,WITH_DEN,8,4>(c, x, y);
+            case 3: return mass_launch_v<NC,WITH_DEN,32,1>(c, x, y);
+            case 4: return mass_launch_v<NC,WITH_DEN,8,6>(c, x, y);
+         }
+      }
+      return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3>(c, x, y);
+   }
    static int mass_h1(Ctx &c, int nc, const double *x, double *y, bool with_den)
    {
       if (nc == 3) { return with_den ? mass_launch<3,true>(c, x, y) : mass_launch<3,false>(c, x, y); }
       if (nc == 1) { return with_den ? mass_launch<1,true>(c, x, y) : mass_launch<1,false>(c, x, y); }
       set_error("mass3d: nc must be 1 or 3"); return LAGB_ERR_INVALID;
    }
+   static int qupdate(Ctx &c, const double *S, const QPointParams &prm)
+   {
+      using Cfg = tuned::QUpd3DCfg<D1D,Q1D>;
+      auto kern = tuned::qupdate3d<D1D,Q1D,NTQ>;
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
+      if (c.NE > c.part_cap) { set_error("qupdate3d: partial buffer too small"); return LAGB_ERR_STATE; }
+      kern<<<c.NE, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
+                                                     c.d_gamma, c.d_qweights, prm, c.d_sJit, c.d_part);
+      LAGB_LAUNCH_CHECK();
+      c.dt_nblocks = c.NE;
+      return LAGB_OK;
+   }
+   static int force_mult(Ctx &c, const double *e, double *v)
+   {
+      using Cfg = tuned::Force3DCfg<D1D,Q1D>;
+      auto kern = tuned::force3d<D1D,Q1D,NTF>;
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
+      kern<<<c.NE, NTF, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
+   static int force_mult_t(Ctx &c, const double *v, double *e)
+   {
+      using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
+      auto kern = tuned::forcet3d<D1D,Q1D,NTF>;
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
+      kern<<<c.NE, NTF, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
+   static int mass_l2(Ctx &c, const double *x, double *y)
+   {
+      using Cfg = tuned::MassL2Cfg<D1D,Q1D>;
+      constexpr int NTE = (Cfg::NQ >= 256) ? 128 : (Cfg::NQ >= 64 ? 64 : 32);
+      constexpr int NB = 256/NTE;
+      auto kern = tuned::massl2_3d<D1D,Q1D,NB,NTE>;
+      constexpr size_t bytes = sizeof(double)*NB*Cfg::PER_ELEM + sizeof(tuned::SmemTables<D1D,Q1D>);
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      kern<<<(c.NE + NB - 1)/NB, NB*NTE, bytes, c.stream>>>(tab(c), c.NE, c.d_massD, x, y);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
+   static void install(KernelSet &ks)
+   {
+      ks.mass_h1 = &mass_h1; ks.qupdate = &qupdate; ks.force_mult = &force_mult;
+      ks.force_mult_t = &force_mult_t; ks.mass_l2 = &mass_l2;
+      ks.tuned_mass = true;
+   }
 };
 
-// <D1D, Q1D, NB for one component, NB for three components>: elements per CTA, chosen
-// so that the shared-memory slab NC*NB*D1D*(Q1D^2+1)*8 B leaves room for several CTAs per SM.
 bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D)
 {
    if (dim != 3) { return false; }
    const int id = (D1D << 4) | Q1D;
    switch (id)
    {
-      case 0x22: ks.mass_h1 = &TunedLaunch3D<2,2,64,32>::mass_h1; break;
-      case 0x34: ks.mass_h1 = &TunedLaunch3D<3,4,32,32>::mass_h1; break;
-      case 0x46: ks.mass_h1 = &TunedLaunch3D<4,6,32,16>::mass_h1; break;
-      case 0x58: ks.mass_h1 = &TunedLaunch3D<5,8,16,8>::mass_h1; break;
-      case 0x6A: ks.mass_h1 = &TunedLaunch3D<6,10,8,4>::mass_h1; break;
+      //                          D  Q  NB1 MB1 NB3 MB3 NTQ  NTF
+      case 0x22: TunedLaunch3D<2, 2, 64, 1, 32, 1,  32,  64>::install(ks); break;
+      case 0x34: TunedLaunch3D<3, 4, 32, 1, 32, 1,  64, 128>::install(ks); break;
+      case 0x46: TunedLaunch3D<4, 6, 32, 2, 16, 3, 216, 256>::install(ks); break;
+      case 0x58: TunedLaunch3D<5, 8, 16, 1,  8, 1, 256, 256>::install(ks); break;
+      case 0x6A: TunedLaunch3D<6, 10, 8, 1,  4, 1, 256, 256>::install(ks); break;
       default: return false;
    }
-   ks.tuned_mass = true;
    return true;
 }
 

@@ -23,6 +23,8 @@
 #include <limits>
 #include <functional>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
 
 namespace oracle {
 
@@ -480,17 +482,72 @@ static inline KernelTable get_table(int dim, int D1D, int Q1D)
 
 // element-parallel helper (stand-in for `mpirun -np <cores>`); threads = 1 is the
 // serial reference path.  Scatter kernels are run serially unless coloured.
+// Persistent worker pool: a fork-join per call would cost more than the kernels at high
+// thread counts (128-core GPU hosts).
+struct WorkerPool
+{
+   std::vector<std::thread> workers;
+   std::mutex mtx; std::condition_variable cv_start, cv_done;
+   const std::function<void(int,int)> *job = nullptr;
+   int job_n = 0, job_parts = 0, generation = 0, pending = 0;
+   bool stop = false;
+   void worker(int id)
+   {
+      int seen = 0;
+      for (;;)
+      {
+         const std::function<void(int,int)> *f; int n, parts;
+         {
+            std::unique_lock<std::mutex> lk(mtx);
+            cv_start.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) { return; }
+            seen = generation; f = job; n = job_n; parts = job_parts;
+         }
+         if (id < parts - 1)
+         {
+            const int a = (int)((long long)n*id/parts), b = (int)((long long)n*(id + 1)/parts);
+            (*f)(a, b);
+         }
+         {
+            std::lock_guard<std::mutex> lk(mtx);
+            if (--pending == 0) { cv_done.notify_one(); }
+         }
+      }
+   }
+   void ensure(int n)
+   {
+      while ((int)workers.size() < n) { const int id = (int)workers.size(); workers.emplace_back([this, id] { worker(id); }); }
+   }
+   // run f over [0,n) split into `parts` contiguous chunks (chunk 0 on the caller)
+   void run(int n, int parts, const std::function<void(int,int)> &f)
+   {
+      ensure(parts - 1);
+      {
+         std::lock_guard<std::mutex> lk(mtx);
+         job = &f; job_n = n; job_parts = parts; pending = (int)workers.size(); generation++;
+      }
+      cv_start.notify_all();
+      // the caller takes the LAST chunk (workers take chunks 0..parts-2 by id)
+      { const int id = parts - 1; const int a = (int)((long long)n*id/parts), b = (int)((long long)n*(id + 1)/parts); f(a, b); }
+      std::unique_lock<std::mutex> lk(mtx);
+      cv_done.wait(lk, [&] { return pending == 0; });
+   }
+   ~WorkerPool()
+   {
+      { std::lock_guard<std::mutex> lk(mtx); stop = true; }
+      cv_start.notify_all();
+      for (auto &w : workers) { w.join(); }
+   }
+};
+inline WorkerPool &worker_pool() { static WorkerPool p; return p; }
+
 inline void parallel_elements(int NE, int nthreads, const std::function<void(int,int)> &f)
 {
    if (nthreads <= 1 || NE < 2) { f(0, NE); return; }
    const int nt = std::min(nthreads, NE);
-   std::vector<std::thread> th;
-   for (int t = 0; t < nt; t++)
-   {
-      const int a = (int)((long long)NE*t/nt), b = (int)((long long)NE*(t + 1)/nt);
-      th.emplace_back([a, b, &f]() { f(a, b); });
-   }
-   for (auto &x : th) { x.join(); }
+   // workers with id >= parts - 1 idle; chunk parts-1 runs on the caller
+   WorkerPool &p = worker_pool();
+   p.run(NE, nt, [&](int a, int b) { f(a, b); });
 }
 
 // ---------------------------------------------------------------------------
@@ -600,6 +657,28 @@ struct Hydro
 
    // MFEM CGSolver::Mult restated.  Returns final_iter.
    // prec == nullptr: unpreconditioned.  iterative_mode: r = b - A x.
+   // vector loops of the CG: serial (the reference's order) for nthreads == 1, chunked over
+   // the worker pool otherwise (what `mpirun -np <cores>` does to MFEM's vector kernels)
+   template<typename F> void vec_for(int64_t n, F f) const
+   {
+      if (nthreads <= 1 || n < 65536) { f((int64_t)0, n); return; }
+      parallel_elements((int)n, nthreads, [&](int a, int b) { f((int64_t)a, (int64_t)b); });
+   }
+   double pdot(const double *a, const double *b, int64_t n) const
+   {
+      if (nthreads <= 1 || n < 65536) { return dot(a, b, n); }
+      const int parts = (int)std::min<int64_t>(nthreads, n);
+      std::vector<double> part(parts, 0.0);
+      parallel_elements((int)n, nthreads, [&](int lo, int hi)
+      {
+         const int id = (int)(((long long)lo*parts + n - 1)/n);
+         part[id] = dot(a + lo, b + lo, hi - lo);
+      });
+      double s = 0.0;
+      for (double v : part) { s += v; }   // fixed chunk order
+      return s;
+   }
+
    int CG(const std::function<void(const double*, double*)> &A, const double *prec,
           bool iterative_mode, const double *b, double *x, int64_t n,
           double *r, double *d, double *z) const
@@ -608,42 +687,40 @@ struct Hydro
       if (iterative_mode)
       {
          A(x, r);
-         for (int64_t i = 0; i < n; i++) { r[i] = b[i] - r[i]; }
+         vec_for(n, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; i++) { r[i] = b[i] - r[i]; } });
       }
       else
       {
-         for (int64_t i = 0; i < n; i++) { r[i] = b[i]; x[i] = 0.0; }
+         vec_for(n, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; i++) { r[i] = b[i]; x[i] = 0.0; } });
       }
-      if (prec) { for (int64_t i = 0; i < n; i++) { z[i] = prec[i]*r[i]; d[i] = z[i]; } }
-      else { for (int64_t i = 0; i < n; i++) { d[i] = r[i]; } }
-      double nom = dot(d, r, n);
+      if (prec) { vec_for(n, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; i++) { z[i] = prec[i]*r[i]; d[i] = z[i]; } }); }
+      else { vec_for(n, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; i++) { d[i] = r[i]; } }); }
+      double nom = pdot(d, r, n);
       if (nom < 0.0) { return 0; }
       const double r0 = std::max(nom*rel_tol*rel_tol, abs_tol*abs_tol);
       if (nom <= r0) { return 0; }
       A(d, z);
-      double den = dot(z, d, n);
+      double den = pdot(z, d, n);
       if (den <= 0.0) { if (den == 0.0) { return 0; } }
       int final_iter = cg_max_iter;
       for (int i = 1; true; )
       {
          const double alpha = nom/den;
-         for (int64_t k = 0; k < n; k++) { x[k] = x[k] + alpha*d[k]; }
-         for (int64_t k = 0; k < n; k++) { r[k] = r[k] - alpha*z[k]; }
-         double betanom;
-         if (prec)
+         vec_for(n, [&](int64_t lo, int64_t hi)
          {
-            for (int64_t k = 0; k < n; k++) { z[k] = prec[k]*r[k]; }
-            betanom = dot(r, z, n);
-         }
-         else { betanom = dot(r, r, n); }
+            for (int64_t k = lo; k < hi; k++) { x[k] = x[k] + alpha*d[k]; }
+            for (int64_t k = lo; k < hi; k++) { r[k] = r[k] - alpha*z[k]; }
+            if (prec) { for (int64_t k = lo; k < hi; k++) { z[k] = prec[k]*r[k]; } }
+         });
+         const double betanom = prec ? pdot(r, z, n) : pdot(r, r, n);
          if (betanom < 0.0) { final_iter = i; break; }
          if (betanom <= r0) { final_iter = i; break; }
          if (++i > cg_max_iter) { break; }
          const double beta = betanom/nom;
-         if (prec) { for (int64_t k = 0; k < n; k++) { d[k] = z[k] + beta*d[k]; } }
-         else { for (int64_t k = 0; k < n; k++) { d[k] = r[k] + beta*d[k]; } }
+         if (prec) { vec_for(n, [&](int64_t lo, int64_t hi) { for (int64_t k = lo; k < hi; k++) { d[k] = z[k] + beta*d[k]; } }); }
+         else { vec_for(n, [&](int64_t lo, int64_t hi) { for (int64_t k = lo; k < hi; k++) { d[k] = r[k] + beta*d[k]; } }); }
          A(d, z);
-         den = dot(d, z, n);
+         den = pdot(d, z, n);
          if (den <= 0.0) { if (den == 0.0) { final_iter = i; break; } }
          nom = betanom;
       }

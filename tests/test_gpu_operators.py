@@ -60,7 +60,7 @@ def perturbed_state(P, seed=1234):
 def test_setup_qdata0(pair):
     P, O, ctxs = pair
     for c in ctxs:
-        assert abs(c.h0 - O.h0) <= 1e-14 * O.h0
+        assert abs(c.h0 - O.h0) <= 1e-13 * O.h0
         for which in (1, 2, 3, 4):
             assert relerr(c.qdata(which).cpu().numpy(), O.qdata(which)) < 1e-13
 

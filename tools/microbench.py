@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Per-operator timings on one GPU (CUDA events, L2-cold: every operator streams > L2 of data).
+
+    python tools/microbench.py [--rs 5] [--ok 3] [--reps 10]
+
+Prints one line per operator: average microseconds, algorithmic GB, GB/s and
+fraction of the measured HBM peak.  Used to pick launch variants (lagb_tune_set).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rs", type=int, default=5)
+    ap.add_argument("--ok", type=int, default=3)
+    ap.add_argument("--mesh", default="cube01_hex")
+    ap.add_argument("--problem", type=int, default=1)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--mass-variants", default="0,1,2,3,4")
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    from laghos_b200.api import Problem, Context
+    peak = 6488.7
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    P = Problem(args.mesh, args.rs, args.problem, args.ok, args.ok - 1)
+    c = Context(P)
+    NE, NQ, nd, nl = P.NE, P.NQ, P.ndofs_h1, P.ndofs_l2
+    rng = np.random.default_rng(1)
+    S = P.S0.copy()
+    nv = P.h1_vsize
+    S[nv:2 * nv] = 0.01 * rng.uniform(-1, 1, nv)
+    S[2 * nv:] = rng.uniform(0.5, 1.5, nl)
+    dS = c.dev(S)
+    v = c.dev(rng.uniform(-1, 1, nv))
+    e = c.dev(rng.uniform(0.5, 1.5, nl))
+    x1 = c.dev(rng.uniform(-1, 1, nd))
+    yv = c.empty(nv)
+    c.qupdate(dS)
+
+    def timeit(fn, reps=args.reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+        return 1e3 * ts[len(ts) // 2]
+
+    rows = []
+
+    def report(name, us, gbytes):
+        bw = gbytes / (us * 1e-6)
+        rows.append((name, us, gbytes, bw, bw / peak))
+        print(f"{name:34s} {us:10.1f} us  {gbytes:7.3f} GB  {bw:8.1f} GB/s  {100 * bw / peak:5.1f}% of {peak:.0f}", flush=True)
+
+    dim = P.dim
+    report("qupdate (fused)", timeit(lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
+           8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)))
+    report("force_mult", timeit(lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
+           8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+    ye = c.empty(nl)
+    report("force_mult_transpose", timeit(lambda: c.lib.lagb_force_mult_transpose(c.h, c._p(v), c._p(ye))),
+           8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+    y1 = c.empty(nd)
+    report("vmass_mult (1 comp)", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
+           8e-9 * (NE * NQ + 2 * nd))
+    for var in [int(s) for s in args.mass_variants.split(",")]:
+        c.tune(0, var)
+        report(f"vmass_mult_all (3 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
+               8e-9 * (NE * NQ + 2 * dim * nd))
+    c.tune(0, 0)
+    report("emass_mult (L2)", timeit(lambda: c.lib.lagb_emass_mult(c.h, c._p(e), c._p(ye))), 8e-9 * (NE * NQ + 2 * nl))
+    b = c.dev(rng.uniform(-1, 1, nv))
+    xs = c.zeros(nv)
+
+    def pcg():
+        xs.zero_()
+        c.pcg_vmass_all(b, xs)
+
+    us = timeit(pcg, 3)
+    _, its = c.pcg_vmass_all(b, c.zeros(nv))
+    nit = max(its)
+    print(f"pcg_vmass_all: {us:.1f} us for {its} iterations -> {us / (nit + 1):.1f} us per iteration", flush=True)
+    bl = c.dev(rng.uniform(-1, 1, nl))
+    us = timeit(lambda: c.cg_emass(bl), 3)
+    _, it2 = c.cg_emass(bl)
+    print(f"cg_emass: {us:.1f} us for {it2} iterations -> {us / max(it2, 1):.1f} us per iteration", flush=True)
+    c.close()
+
+
+if __name__ == "__main__":
+    main()
