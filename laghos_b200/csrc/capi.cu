@@ -345,6 +345,11 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    rc |= dev_upload(&c.d_map, d->h_h1_map, (size_t)c.NE*c.ND);
    for (int k = 0; k < c.dim; k++) { c.ness[k] = d->ness[k]; rc |= dev_upload(&c.d_ess[k], d->h_ess[k], (size_t)d->ness[k]); }
    rc |= dev_upload(&c.d_qweights, d->h_qweights, (size_t)c.NQ);
+   {
+      std::vector<double> iw(c.NQ);
+      for (int q = 0; q < c.NQ; q++) { iw[q] = 1.0/d->h_qweights[q]; }
+      rc |= dev_upload(&c.d_inv_qweights, iw.data(), (size_t)c.NQ);
+   }
    rc |= dev_upload(&c.d_gamma, d->h_gamma, (size_t)c.NE);
    rc |= dev_alloc(&c.d_sJit, NEQ*D2); rc |= dev_alloc(&c.d_rho0DetJ0w, NEQ);
    rc |= dev_alloc(&c.d_Jac0inv, NEQ*D2); rc |= dev_alloc(&c.d_massD, NEQ);
@@ -370,7 +375,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    if (!h) { return; }
    Ctx &c = h->c;
    cudaStreamSynchronize(c.stream);
-   void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
+   void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_inv_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
                    c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinvm, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
                    c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
@@ -510,7 +515,7 @@ int lagb_qupdate_async(lagb_ctx *h, const double *d_S, double cfl)
    if (!c.setup_done) { set_error("qupdate: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    QPointParams prm;
-   prm.h0 = c.h0; prm.h1order = (double)(c.D1D - 1); prm.cfl = cfl; prm.dt_in = std::numeric_limits<double>::infinity();
+   prm.h0 = c.h0; prm.h1order = (double)(c.D1D - 1); prm.inv_h1order = 1.0/prm.h1order; prm.cfl = cfl; prm.dt_in = std::numeric_limits<double>::infinity();
    prm.use_viscosity = c.use_visc; prm.use_vorticity = c.use_vort;
    int rc = timer_begin(c, 3); if (rc) { return rc; }
    rc = ks.qupdate(c, d_S, prm); if (rc) { return rc; }

@@ -54,7 +54,7 @@ struct Ctx
    std::vector<unsigned char> tab_blob;   // DevTables<D1D,Q1D> bytes
    // device arrays
    int *d_map = nullptr; int *d_ess[3] = {nullptr, nullptr, nullptr}; int ness[3] = {0, 0, 0};
-   double *d_qweights = nullptr, *d_gamma = nullptr;
+   double *d_qweights = nullptr, *d_inv_qweights = nullptr, *d_gamma = nullptr;
    double *d_sJit = nullptr, *d_rho0DetJ0w = nullptr, *d_Jac0inv = nullptr, *d_massD = nullptr;
    double *d_diag = nullptr, *d_dinvm = nullptr;     // [ndofs], [dim*ndofs] (masked)
    double *d_r = nullptr, *d_d = nullptr, *d_z = nullptr;      // [dim*ndofs]

@@ -47,7 +47,7 @@ __device__ __forceinline__ void contract(const double *T, const double *in, doub
 
 struct QPointParams
 {
-   double h0, h1order, cfl, dt_in;
+   double h0, h1order, inv_h1order, cfl, dt_in;
    int use_viscosity, use_vorticity;
 };
 
@@ -58,7 +58,7 @@ struct QPointParams
 template<int DIM>
 __device__ __forceinline__ double qpoint(const double *J, const double *dV, const double e_q,
                                          const double rho0DetJ0w, const double *J0inv,
-                                         const double gamma, const double weight,
+                                         const double gamma, const double weight, const double inv_weight,
                                          const QPointParams &p, double *sJ)
 {
    constexpr int DIM2 = DIM*DIM;
@@ -84,8 +84,8 @@ __device__ __forceinline__ double qpoint(const double *J, const double *dV, cons
       Jinv[7] = (J[6]*J[1] - J[7]*J[0])*t;
       Jinv[8] = (J[0]*J[4] - J[1]*J[3])*t;
    }
-   const double inv_weight = 1./weight;
-   const double R = inv_weight*rho0DetJ0w/detJ;
+   const double idetJ = 1.0/detJ;
+   const double R = inv_weight*rho0DetJ0w*idetJ;  // reference laghos_solver.cpp:1081 (inv_weight*rho0DetJ0w/detJ)
    const double E = fmax(0.0, e_q);
    const double P = (gamma - 1.0)*R*E;
    const double S = sqrt(gamma*(gamma - 1.0)*E);
@@ -176,7 +176,7 @@ __device__ __forceinline__ double qpoint(const double *J, const double *dV, cons
    const double sv = (DIM == 2) ? qm::min_sv2(J[0], J[1], J[2], J[3])
                      : qm::min_sv3(J[0], J[1], J[2], J[3], J[DIM2 > 4 ? 4 : 0], J[DIM2 > 5 ? 5 : 0],
                                    J[DIM2 > 6 ? 6 : 0], J[DIM2 > 7 ? 7 : 0], J[DIM2 > 8 ? 8 : 0]);
-   const double h_min = sv/p.h1order;
+   const double h_min = sv*p.inv_h1order;
    const double ih_min = 1./h_min;
    const double irho_ih_min_sq = ih_min*ih_min/R;
    const double idt = S*ih_min + 2.5*visc_coeff*irho_ih_min_sq;

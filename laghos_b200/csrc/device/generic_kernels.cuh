@@ -314,7 +314,7 @@ __global__ void qupdate(const __grid_constant__ DevTables<D1D,Q1D> tab, int NE, 
                const size_t eq = (size_t)e*Dm::NQ + q;
                double J0[DIM2], sJ[DIM2];
                for (int k = 0; k < DIM2; k++) { J0[k] = Jac0inv[eq*DIM2 + k]; }
-               const double dtq = qpoint<DIM>(J, dV, e_q, rho0DetJ0w[eq], J0, gam, qweights[q], prm, sJ);
+               const double dtq = qpoint<DIM>(J, dV, e_q, rho0DetJ0w[eq], J0, gam, qweights[q], 1.0/qweights[q], prm, sJ);
                dt_min = fmin(dt_min, dtq);
                for (int vd = 0; vd < DIM; vd++)
                   for (int gd = 0; gd < DIM; gd++) { sJit[eq + NEQ*(gd + vd*DIM)] = sJ[vd + gd*DIM]; }

@@ -6,8 +6,9 @@
 //   * NC*D1D threads per element, NB elements per CTA, NC velocity components per pass
 //     (NC = 3 in the batched PCG: the quadrature data D is read ONCE for all three
 //     component solves of SolveVelocity, laghos_solver.cpp:363-398).
-//   * phase A  thread (c,e,dz) gathers the xy-slice dz of component c straight from the
-//              L-vector through the restriction map, contracts x then y in registers
+//   * phase 0  all threads gather the CTA's element dofs with lanes along the element-local
+//              dof index (4x fewer L1 sectors per request than a per-slice gather);
+//   * phase A  thread (c,e,dz) contracts x then y of slice dz of component c in registers
 //              (B in the kernel-parameter constant bank, fully unrolled) and stores the
 //              Q1D^2 plane to shared memory;
 //   * phase B  flat (element,column) index over the CTA's NB*Q1D^2 quadrature columns:
@@ -15,8 +16,9 @@
 //              of D touched once), contract z back (Q1D -> D1D), in registers, in place
 //              in shared memory; optionally accumulates d^t A d = sum_q D u_q^2 for the
 //              PCG denominator at no extra memory traffic;
-//   * phase C  thread (c,e,dz) contracts y then x back to dofs and scatter-adds to the
-//              L-vector (red.global.add.f64).
+//   * phase C  thread (c,e,dz) contracts y then x back to dofs;
+//   * phase D  all threads scatter-add to the L-vector (red.global.add.f64), lanes along the
+//              dof index so that the D1D entries of a lattice row share one L2 sector.
 //   Shared memory traffic is 4*D1D*Q1D^2 doubles per element and component (no
 //   per-FMA shared operands); every thread is active in every phase.
 #pragma once
@@ -34,9 +36,9 @@ struct Mass3DCfg
    static constexpr int T = ((TA + 31)/32)*32;      // CTA size, padded to whole warps
    static constexpr int NCOL = (NB*QQ + T - 1)/T;   // quadrature columns per thread in phase B
    static constexpr bool PREFETCH = (NCOL*Q1D <= 24); // hold the columns' D values in registers across phase A
-   static constexpr int PLANE = QQ + 1;             // padded plane stride (odd: conflict-free 64-bit)
+   static constexpr int PLANE = ((QQ > DD ? QQ : DD) | 1);   // plane stride (odd: conflict-free 64-bit)
    static constexpr int SMEM_DOUBLES = NC*NB*D1D*PLANE;
-   static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double);
+   static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*ND*sizeof(int);
 };
 
 template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB>
@@ -47,13 +49,14 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
 {
    using C = Mass3DCfg<D1D,Q1D,NB,NC>;
    extern __shared__ double sV[];   // [c][e_loc][dz][PLANE]
+   int *sIdx = reinterpret_cast<int*>(sV + C::SMEM_DOUBLES);   // [e_loc][ND]
    const int t = threadIdx.x;
    const int c = t / C::TG, r = t - c*C::TG;
    const int e_loc = r / D1D, dz = r % D1D;
    const int eb = blockIdx.x*NB;
-   const int e = eb + e_loc;
-   const bool active = (t < C::TA) && (e < NE);
-   const int ncols = min(NB, NE - eb)*C::QQ;
+   const int nel = min(NB, NE - eb);
+   const bool active = (t < C::TA) && (e_loc < nel);
+   const int ncols = nel*C::QQ;
 
    // quadrature data of this thread's phase-B columns: issued first so that the DRAM
    // latency overlaps the gather and phase A
@@ -70,22 +73,33 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
          for (int qz = 0; qz < Q1D; qz++) { dq[k][qz] = __ldg(dptr + C::QQ*qz); }
       }
    }
-   int idx[C::DD];
+   // ---- phase 0: cooperative gather, lanes along the element-local dof index (runs of D1D
+   //      contiguous L-vector entries per lattice row).  Slice (c,e,dz) is parked in the
+   //      first DD slots of its own plane.
+   for (int it = t; it < nel*C::ND; it += C::T)
+   {
+      const int e2 = it / C::ND, i = it - e2*C::ND;
+      const int id = __ldg(map + (size_t)eb*C::ND + it);
+      sIdx[it] = id;
+      const int z = i / C::DD, ixy = i - z*C::DD;
+#pragma unroll
+      for (int cc = 0; cc < NC; cc++)
+      {
+         sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy] = x[(size_t)cc*cstride + id];
+      }
+   }
+   __syncthreads();
    double *pl = sV + ((size_t)(c*NB + e_loc)*D1D + dz)*C::PLANE;
-   // ---- phase A: gather slice, x then y contraction, store plane ----
+   // ---- phase A: x then y contraction of the slice, store plane ----
    if (active)
    {
-      const int *m = map + (size_t)e*C::ND + dz*C::DD;
-#pragma unroll
-      for (int i = 0; i < C::DD; i++) { idx[i] = m[i]; }
-      const double *xc = x + (size_t)c*cstride;
       double U[Q1D][D1D];
 #pragma unroll
       for (int dy = 0; dy < D1D; dy++)
       {
          double X[D1D];
 #pragma unroll
-         for (int dx = 0; dx < D1D; dx++) { X[dx] = xc[idx[dx + D1D*dy]]; }
+         for (int dx = 0; dx < D1D; dx++) { X[dx] = pl[dx + D1D*dy]; }
 #pragma unroll
          for (int qx = 0; qx < Q1D; qx++)
          {
@@ -154,7 +168,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
       }
    }
    __syncthreads();
-   // ---- phase C: y then x back, scatter-add ----
+   // ---- phase C: y then x back; the slice result overwrites the first DD plane slots ----
    if (active)
    {
       double Z[Q1D][D1D];
@@ -173,7 +187,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
             Z[qx][dy] = z;
          }
       }
-      double *yc = y + (size_t)c*cstride;
+      // all plane reads of this thread are complete (Z holds them): safe to overwrite
 #pragma unroll
       for (int dy = 0; dy < D1D; dy++)
 #pragma unroll
@@ -182,8 +196,21 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
             double o = 0.0;
 #pragma unroll
             for (int qx = 0; qx < Q1D; qx++) { o += tab.B[qx + Q1D*dx]*Z[qx][dy]; }
-            atomicAdd(yc + idx[dx + D1D*dy], o);
+            pl[dx + D1D*dy] = o;
          }
+   }
+   __syncthreads();
+   // ---- phase D: cooperative scatter-add (red.global.add.f64), lanes along the dof index ----
+   for (int it = t; it < nel*C::ND; it += C::T)
+   {
+      const int e2 = it / C::ND, i = it - e2*C::ND;
+      const int id = sIdx[it];
+      const int z = i / C::DD, ixy = i - z*C::DD;
+#pragma unroll
+      for (int cc = 0; cc < NC; cc++)
+      {
+         atomicAdd(y + (size_t)cc*cstride + id, sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy]);
+      }
    }
    if (WITH_DEN)
    {

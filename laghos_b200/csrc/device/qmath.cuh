@@ -5,7 +5,10 @@
 // adjugate inverse, scaled closed-form symmetric eigen-solver (trigonometric root
 // of the characteristic polynomial that is best separated, deflation by its
 // eigenvector, Parlett's 2x2 rotation), smallest singular value through the
-// eigenvalues of J^t J.  QUpdateBody only consumes the smallest eigenvalue and its
+// eigenvalues of J^t J.  Divisions by 3, 6 and by the power-of-two scaling factor are
+// written as multiplications (<= 1 ulp from MFEM's quotients, far inside the parity
+// tolerance): an fp64 division costs ~20 instructions on the GPU and QUpdate is
+// instruction-bound.  QUpdateBody only consumes the smallest eigenvalue and its
 // eigenvector (compr_dir, laghos_solver.cpp:1113-1124), so only that pair is
 // returned.  Written with scalars and selects (no dynamically indexed arrays) so
 // everything stays in registers.  Column-major like MFEM.
@@ -30,6 +33,26 @@ LAGB_HD double scaling_factor(double d_max)
    return 1.0;
 }
 
+// The same power of two 2^e (d_max = m 2^e, m in [0.5,1)) built from the exponent bits,
+// together with its exact inverse: x/mult == x*inv bit for bit, and a multiplication costs a
+// tenth of an fp64 division on the GPU.  Zero / subnormal / huge d_max (never reached by
+// physical Jacobians) fall back to the generic routine.
+LAGB_HD void scaling_factor_inv(double d_max, double &mult, double &inv)
+{
+#ifdef __CUDA_ARCH__
+   const long long bits = __double_as_longlong(d_max);
+   const long long be = (bits >> 52) & 0x7ff;            // biased exponent of d_max (d_max >= 0)
+   if (be >= 2 && be <= 2040)
+   {
+      mult = __longlong_as_double((be + 1) << 52);       // 2^(be+1-1023) = 2^e
+      inv = __longlong_as_double((2046 - (be + 1)) << 52);
+      return;
+   }
+#endif
+   mult = scaling_factor(d_max);
+   inv = 1.0/mult;
+}
+
 // Parlett: rotation diagonalising [d1 d12; d12 d2]; eigenvectors (c,-s), (s,c)
 LAGB_HD void eigensystem2s(const double d12, double &d1, double &d2, double &c, double &s)
 {
@@ -40,7 +63,11 @@ LAGB_HD void eigensystem2s(const double d12, double &d1, double &d2, double &c, 
    const double azeta = fabs(zeta);
    if (azeta < sqrt_1_eps) { t = copysign(1.0/(azeta + sqrt(1.0 + zeta*zeta)), zeta); }
    else { t = copysign(0.5/azeta, zeta); }
+#ifdef __CUDA_ARCH__
+   c = rsqrt(1.0 + t*t);
+#else
    c = sqrt(1.0/(1.0 + t*t));
+#endif
    s = c*t;
    t *= d12;
    d1 -= t;
@@ -63,7 +90,11 @@ LAGB_HD bool kernel_vector3s(double c1, double c2, double c3, double d12, double
    if (ne > n) { n = ne; z0 = e0; z1 = e1; z2 = e2; }
    const double amax = fmax(fmax(fmax(fabs(c1), fabs(c2)), fmax(fabs(c3), fabs(d12))), fmax(fabs(d13), fabs(d23)));
    if (!(n > 1e-28*amax*amax*amax*amax) || n == 0.0) { return false; }
+#ifdef __CUDA_ARCH__
+   const double inv = rsqrt(n);
+#else
    const double inv = 1.0/sqrt(n);
+#endif
    z0 *= inv; z1 *= inv; z2 *= inv;
    return true;
 }
@@ -84,12 +115,13 @@ LAGB_HD void complete_basis(double z0, double z1, double z2,
    const double vi1 = (k == 0) ? v1 : (k == 1) ? v2 : v0;
    const double vi2 = (k == 0) ? v2 : (k == 1) ? v0 : v1;
    const int i1 = (k + 1) % 3, i2 = (k + 2) % 3;
-   u0 = ((i1 == 0) ? 1.0 : 0.0) - 2.0*v0*vi1/vn2;
-   u1 = ((i1 == 1) ? 1.0 : 0.0) - 2.0*v1*vi1/vn2;
-   u2 = ((i1 == 2) ? 1.0 : 0.0) - 2.0*v2*vi1/vn2;
-   w0 = ((i2 == 0) ? 1.0 : 0.0) - 2.0*v0*vi2/vn2;
-   w1 = ((i2 == 1) ? 1.0 : 0.0) - 2.0*v1*vi2/vn2;
-   w2 = ((i2 == 2) ? 1.0 : 0.0) - 2.0*v2*vi2/vn2;
+   const double f1 = 2.0*vi1/vn2, f2 = 2.0*vi2/vn2;
+   u0 = ((i1 == 0) ? 1.0 : 0.0) - v0*f1;
+   u1 = ((i1 == 1) ? 1.0 : 0.0) - v1*f1;
+   u2 = ((i1 == 2) ? 1.0 : 0.0) - v2*f1;
+   w0 = ((i2 == 0) ? 1.0 : 0.0) - v0*f2;
+   w1 = ((i2 == 1) ? 1.0 : 0.0) - v1*f2;
+   w2 = ((i2 == 2) ? 1.0 : 0.0) - v2*f2;
 }
 
 // smallest eigenvalue and its unit eigenvector of the symmetric 2x2 (a d; d b)
@@ -107,12 +139,14 @@ LAGB_HD void min_eig3(double d11, double d12, double d13, double d22, double d23
                       double &lmin, double &x0, double &x1, double &x2)
 {
    const double d_max = fmax(fmax(fmax(fabs(d11), fabs(d22)), fmax(fabs(d33), fabs(d12))), fmax(fabs(d13), fabs(d23)));
-   const double mult = scaling_factor(d_max);
-   d11 /= mult; d22 /= mult; d33 /= mult;
-   d12 /= mult; d13 /= mult; d23 /= mult;
-   double aa = (d11 + d22 + d33)/3;
+   if (d_max == 0.0) { lmin = 0.0; x0 = 1.0; x1 = 0.0; x2 = 0.0; return; }   // zero matrix: what the general path returns
+   double mult, imult;
+   scaling_factor_inv(d_max, mult, imult);
+   d11 *= imult; d22 *= imult; d33 *= imult;
+   d12 *= imult; d13 *= imult; d23 *= imult;
+   double aa = (d11 + d22 + d33)*(1.0/3.0);
    double c1 = d11 - aa, c2 = d22 - aa, c3 = d33 - aa;
-   const double Q = (2*(d12*d12 + d13*d13 + d23*d23) + c1*c1 + c2*c2 + c3*c3)/6;
+   const double Q = (2*(d12*d12 + d13*d13 + d23*d23) + c1*c1 + c2*c2 + c3*c3)*(1.0/6.0);
    double R = (c1*(d23*d23 - c2*c3) + d12*(d12*c3 - 2*d13*d23) + d13*d13*c2)/2;
    bool ident = true;
    if (Q > 0.)
@@ -124,8 +158,8 @@ LAGB_HD void min_eig3(double d11, double d12, double d13, double d22, double d23
       else
       {
          R = R/sqrtQ3;
-         if (R < 0.) { r = -2*sqrtQ*cos((acos(R) + 2.0*M_PI)/3); }
-         else        { r = -2*sqrtQ*cos(acos(R)/3); }
+         if (R < 0.) { r = -2*sqrtQ*cos((acos(R) + 2.0*M_PI)*(1.0/3.0)); }
+         else        { r = -2*sqrtQ*cos(acos(R)*(1.0/3.0)); }
       }
       aa += r;
       c1 = d11 - aa; c2 = d22 - aa; c3 = d33 - aa;
@@ -175,23 +209,24 @@ LAGB_HD double min_sv3(double d0, double d1, double d2, double d3, double d4,
 {
    double d_max = fmax(fmax(fmax(fabs(d0), fabs(d1)), fmax(fabs(d2), fabs(d3))),
                        fmax(fmax(fabs(d4), fabs(d5)), fmax(fabs(d6), fmax(fabs(d7), fabs(d8)))));
-   const double mult = scaling_factor(d_max);
-   d0 /= mult; d1 /= mult; d2 /= mult; d3 /= mult; d4 /= mult;
-   d5 /= mult; d6 /= mult; d7 /= mult; d8 /= mult;
+   double mult, imult;
+   scaling_factor_inv(d_max, mult, imult);
+   d0 *= imult; d1 *= imult; d2 *= imult; d3 *= imult; d4 *= imult;
+   d5 *= imult; d6 *= imult; d7 *= imult; d8 *= imult;
    const double b11 = d0*d0 + d1*d1 + d2*d2;
    const double b12 = d0*d3 + d1*d4 + d2*d5;
    const double b13 = d0*d6 + d1*d7 + d2*d8;
    const double b22 = d3*d3 + d4*d4 + d5*d5;
    const double b23 = d3*d6 + d4*d7 + d5*d8;
    const double b33 = d6*d6 + d7*d7 + d8*d8;
-   double aa = (b11 + b22 + b33)/3;
+   double aa = (b11 + b22 + b33)*(1.0/3.0);
    const double b11_b22 = ((d0 - d3)*(d0 + d3) + (d1 - d4)*(d1 + d4) + (d2 - d5)*(d2 + d5));
    const double b22_b33 = ((d3 - d6)*(d3 + d6) + (d4 - d7)*(d4 + d7) + (d5 - d8)*(d5 + d8));
    const double b33_b11 = ((d6 - d0)*(d6 + d0) + (d7 - d1)*(d7 + d1) + (d8 - d2)*(d8 + d2));
-   const double c1 = (b11_b22 - b33_b11)/3;
-   const double c2 = (b22_b33 - b11_b22)/3;
-   const double c3 = (b33_b11 - b22_b33)/3;
-   const double Q = (2*(b12*b12 + b13*b13 + b23*b23) + c1*c1 + c2*c2 + c3*c3)/6;
+   const double c1 = (b11_b22 - b33_b11)*(1.0/3.0);
+   const double c2 = (b22_b33 - b11_b22)*(1.0/3.0);
+   const double c3 = (b33_b11 - b22_b33)*(1.0/3.0);
+   const double Q = (2*(b12*b12 + b13*b13 + b23*b23) + c1*c1 + c2*c2 + c3*c3)*(1.0/6.0);
    double R = (c1*(b23*b23 - c2*c3) + b12*(b12*c3 - 2*b13*b23) + b13*b13*c2)/2;
    if (Q > 0.)
    {
@@ -203,9 +238,9 @@ LAGB_HD double min_sv3(double d0, double d1, double d2, double d3, double d4,
       else
       {
          R = R/sqrtQ3;
-         if (fabs(R) <= 0.9) { aa -= 2*sqrtQ*cos(acos(R)/3); have_aa = true; }
-         else if (R < 0.) { r = -2*sqrtQ*cos((acos(R) + 2.0*M_PI)/3); }
-         else { r = -2*sqrtQ*cos(acos(R)/3); aa += r; have_aa = true; }
+         if (fabs(R) <= 0.9) { aa -= 2*sqrtQ*cos(acos(R)*(1.0/3.0)); have_aa = true; }
+         else if (R < 0.) { r = -2*sqrtQ*cos((acos(R) + 2.0*M_PI)*(1.0/3.0)); }
+         else { r = -2*sqrtQ*cos(acos(R)*(1.0/3.0)); aa += r; have_aa = true; }
       }
       if (!have_aa)
       {
@@ -243,22 +278,33 @@ LAGB_HD double norml2_accum(double &scale, double &sum, double v)
    }
    return 0.0;
 }
+// On the device the 2-norm is taken directly: the arguments are element lengths and unit
+// vectors (|x| in [1e-150, 1e150] cannot over/underflow when squared), and the scaled
+// recurrence above costs three fp64 divisions per call.  Agrees with it to ~1 ulp.
 LAGB_HD double norml2_2(double a, double b)
 {
+#ifdef __CUDA_ARCH__
+   return sqrt(a*a + b*b);
+#else
    double scale = 0.0, sum = 0.0;
    norml2_accum(scale, sum, a); norml2_accum(scale, sum, b);
    return scale*sqrt(sum);
+#endif
 }
 LAGB_HD double norml2_3(double a, double b, double c)
 {
+#ifdef __CUDA_ARCH__
+   return sqrt(a*a + b*b + c*c);
+#else
    double scale = 0.0, sum = 0.0;
    norml2_accum(scale, sum, a); norml2_accum(scale, sum, b); norml2_accum(scale, sum, c);
    return scale*sqrt(sum);
+#endif
 }
 
 LAGB_HD double smooth_step_01(double x, double eps)
 {
-   const double y = (x + eps)/(2.0*eps);
+   const double y = (x + eps)*(0.5/eps);   // eps is a literal at the call site: folded at compile time
    if (y < 0.0) { return 0.0; }
    if (y > 1.0) { return 1.0; }
    return (3.0 - 2.0*y)*y*y;

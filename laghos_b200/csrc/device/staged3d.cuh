@@ -1,7 +1,4 @@
-// Tuned 3D kernels for QUpdate, Force, Force^T and the L2 mass apply: one CTA per
-// element (or per NB elements), every 1D contraction stage distributes its output
-// entries over ALL threads of the CTA ("items"), intermediates live in shared memory,
-// quadrature data is read/written exactly once with q-contiguous (coalesced) accesses.
+// Tuned 3D kernels for QUpdate, Force, Force^T and the L2 mass apply.
 //
 //   qupdate3d   reference QUpdate::UpdateQuadratureData (laghos_solver.cpp:1354-1411):
 //               H1R->Mult + q1->Derivatives (x and v) + q2->Values (e) + QKernel fused;
@@ -12,8 +9,14 @@
 //               ForceMultTranspose3D (:715-924) + L2R->MultTranspose fused.
 //   massl2_3d   reference MassPAOperator(L2)::Mult (laghos_solver.cpp:179; MFEM PA mass).
 //
-// Tables are copied to shared memory (they are indexed with per-lane indices, which the
-// constant bank would serialise).
+// Structure ("pencil" sum factorisation): a CTA owns NB elements; every 1D contraction
+// stage is a flat list of pencils (one per line of the tensor along the contracted axis)
+// distributed over all threads.  A pencil loads its N inputs from shared memory once and
+// produces all M outputs in registers, so the 1D tables are compile-time indexed operands
+// from the kernel-parameter constant bank (no table traffic) and shared memory sees
+// (N + M) accesses per N*M FMAs.  Quadrature data (stressJinvT, Jac0inv, rho0DetJ0w, D) is
+// read or written exactly once, q-contiguous (coalesced); L-vector gathers / scatter-adds
+// run with lanes along the element-local dof index.
 #pragma once
 #include "common.cuh"
 #include <cfloat>
@@ -21,130 +24,157 @@
 namespace lagb {
 namespace tuned {
 
-template<int D1D, int Q1D>
-struct SmemTables
+// out[q] = sum_d T[q + Q*d]*in[d]   (dofs -> quadrature), compile-time table indices
+template<int N1D, int Q1D>
+__device__ __forceinline__ void pencil_fwd(const double *T, const double (&in)[N1D], double (&out)[Q1D])
 {
-   double B[Q1D*D1D], G[Q1D*D1D], BL[Q1D*(D1D > 1 ? D1D - 1 : 1)];
-   __device__ __forceinline__ void load(const DevTables<D1D,Q1D> &tab, int tid, int nthr)
+#pragma unroll
+   for (int q = 0; q < Q1D; q++)
    {
-      for (int i = tid; i < Q1D*D1D; i += nthr) { B[i] = tab.B[i]; G[i] = tab.G[i]; }
-      for (int i = tid; i < Q1D*(D1D - 1); i += nthr) { BL[i] = tab.BL[i]; }
-   }
-};
-
-// ---------------------------------------------------------------------------
-// L2 (Bernstein) values at the quadrature points of one element:
-// E[L1D^3] -> out[Q1D^3], scratch t1[L1D*L1D*Q1D], t2[L1D*Q1D*Q1D].  Ends with a barrier.
-// ---------------------------------------------------------------------------
-template<int L1D, int Q1D>
-__device__ __forceinline__ void l2_values(const double *BL, const double *E, double *t1, double *t2,
-                                          double *out, int tid, int nthr)
-{
-   constexpr int QQ = Q1D*Q1D;
-   for (int it = tid; it < L1D*L1D*Q1D; it += nthr)
-   {
-      const int qx = it % Q1D, r = it / Q1D;   // r = ly + L1D*lz
       double u = 0.0;
 #pragma unroll
-      for (int lx = 0; lx < L1D; lx++) { u += BL[qx + Q1D*lx]*E[lx + L1D*r]; }
-      t1[it] = u;                               // [lz][ly][qx]
-   }
-   __syncthreads();
-   for (int it = tid; it < L1D*QQ; it += nthr)
-   {
-      const int qx = it % Q1D, qy = (it / Q1D) % Q1D, lz = it / QQ;
-      double u = 0.0;
-#pragma unroll
-      for (int ly = 0; ly < L1D; ly++) { u += BL[qy + Q1D*ly]*t1[qx + Q1D*(ly + L1D*lz)]; }
-      t2[it] = u;                               // [lz][qy][qx]
-   }
-   __syncthreads();
-   for (int q = tid; q < Q1D*QQ; q += nthr)
-   {
-      const int col = q % QQ, qz = q / QQ;
-      double u = 0.0;
-#pragma unroll
-      for (int lz = 0; lz < L1D; lz++) { u += BL[qz + Q1D*lz]*t2[col + QQ*lz]; }
+      for (int d = 0; d < N1D; d++) { u += T[q + Q1D*d]*in[d]; }
       out[q] = u;
    }
-   __syncthreads();
 }
-
-// quadrature values -> L2 dofs (transpose of the above): in[Q1D^3] -> out (global, L1D^3)
-template<int L1D, int Q1D>
-__device__ __forceinline__ void l2_values_t(const double *BL, const double *in, double *t2, double *t1,
-                                            double *out, int tid, int nthr)
+// out[d] = sum_q T[q + Q*d]*in[q]   (quadrature -> dofs)
+template<int N1D, int Q1D>
+__device__ __forceinline__ void pencil_bwd(const double *T, const double (&in)[Q1D], double (&out)[N1D])
 {
-   constexpr int QQ = Q1D*Q1D;
-   for (int it = tid; it < L1D*QQ; it += nthr)
+#pragma unroll
+   for (int d = 0; d < N1D; d++)
    {
-      const int col = it % QQ, lz = it / QQ;
       double u = 0.0;
 #pragma unroll
-      for (int qz = 0; qz < Q1D; qz++) { u += BL[qz + Q1D*lz]*in[col + QQ*qz]; }
-      t2[it] = u;                               // [lz][qy][qx]
-   }
-   __syncthreads();
-   for (int it = tid; it < L1D*L1D*Q1D; it += nthr)
-   {
-      const int qx = it % Q1D, ly = (it / Q1D) % L1D, lz = it / (Q1D*L1D);
-      double u = 0.0;
-#pragma unroll
-      for (int qy = 0; qy < Q1D; qy++) { u += BL[qy + Q1D*ly]*t2[qx + Q1D*(qy + Q1D*lz)]; }
-      t1[it] = u;                               // [lz][ly][qx]
-   }
-   __syncthreads();
-   for (int it = tid; it < L1D*L1D*L1D; it += nthr)
-   {
-      const int lx = it % L1D, r = it / L1D;
-      double u = 0.0;
-#pragma unroll
-      for (int qx = 0; qx < Q1D; qx++) { u += BL[qx + Q1D*lx]*t1[qx + Q1D*r]; }
-      out[it] = u;
+      for (int q = 0; q < Q1D; q++) { u += T[q + Q1D*d]*in[q]; }
+      out[d] = u;
    }
 }
 
 // ---------------------------------------------------------------------------
-// Gradient stages shared by qupdate3d and forcet3d: NF scalar H1 fields in
-// Xs[f][D1D^3] -> BB, GB, BG [f][dz][qy][qx] (value, d/dxi0, d/dxi1 before the z pass).
+// L2 (Bernstein) dofs -> values at quadrature points for NB elements.
+// Es[e][NL] -> Eq[e][NQ]; scratch t1[e][L*L*Q], t2[e][L*Q*Q].  Ends with a barrier.
+// ---------------------------------------------------------------------------
+template<int L1D, int Q1D>
+__device__ __forceinline__ void l2_values(const double *BL, int nel, const double *Es, int sE,
+                                          double *t1, int s1, double *t2, int s2, double *Eq, int sQ,
+                                          int tid, int nthr)
+{
+   constexpr int QQ = Q1D*Q1D, LL = L1D*L1D;
+   for (int it = tid; it < nel*LL; it += nthr)            // x pencils (lz, ly)
+   {
+      const int e = it / LL, r = it - e*LL;
+      double in[L1D], out[Q1D];
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { in[l] = Es[e*sE + l + L1D*r]; }
+      pencil_fwd<L1D,Q1D>(BL, in, out);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { t1[e*s1 + q + Q1D*r] = out[q]; }     // [lz][ly][qx]
+   }
+   __syncthreads();
+   for (int it = tid; it < nel*L1D*Q1D; it += nthr)       // y pencils (lz, qx)
+   {
+      const int e = it / (L1D*Q1D), r = it - e*(L1D*Q1D);
+      const int qx = r % Q1D, lz = r / Q1D;
+      double in[L1D], out[Q1D];
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { in[l] = t1[e*s1 + qx + Q1D*(l + L1D*lz)]; }
+      pencil_fwd<L1D,Q1D>(BL, in, out);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { t2[e*s2 + qx + Q1D*(q + Q1D*lz)] = out[q]; }   // [lz][qy][qx]
+   }
+   __syncthreads();
+   for (int it = tid; it < nel*QQ; it += nthr)            // z pencils (column)
+   {
+      const int e = it / QQ, col = it - e*QQ;
+      double in[L1D], out[Q1D];
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { in[l] = t2[e*s2 + col + QQ*l]; }
+      pencil_fwd<L1D,Q1D>(BL, in, out);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { Eq[e*sQ + col + QQ*q] = out[q]; }
+   }
+   __syncthreads();
+}
+
+// y and x pencils of the transposed L2 interpolation: t2[e][lz][qy][qx] -> out (global, [e][NL])
+template<int L1D, int Q1D>
+__device__ __forceinline__ void l2_values_t_yx(const double *BL, int nel, const double *t2, int s2,
+                                               double *t1, int s1, double *out, int tid, int nthr)
+{
+   constexpr int LL = L1D*L1D, NL = LL*L1D;
+   for (int it = tid; it < nel*L1D*Q1D; it += nthr)       // y pencils (lz, qx)
+   {
+      const int e = it / (L1D*Q1D), r = it - e*(L1D*Q1D);
+      const int qx = r % Q1D, lz = r / Q1D;
+      double in[Q1D], o[L1D];
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { in[q] = t2[e*s2 + qx + Q1D*(q + Q1D*lz)]; }
+      pencil_bwd<L1D,Q1D>(BL, in, o);
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { t1[e*s1 + qx + Q1D*(l + L1D*lz)] = o[l]; }   // [lz][ly][qx]
+   }
+   __syncthreads();
+   for (int it = tid; it < nel*LL; it += nthr)            // x pencils (lz, ly)
+   {
+      const int e = it / LL, r = it - e*LL;
+      double in[Q1D], o[L1D];
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { in[q] = t1[e*s1 + q + Q1D*r]; }
+      pencil_bwd<L1D,Q1D>(BL, in, o);
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { out[(size_t)e*NL + l + L1D*r] = o[l]; }
+   }
+}
+
+// ---------------------------------------------------------------------------
+// x and y pencils of the H1 gradient for NF fields per element:
+// Xs[e][f][ND] -> Bx,Gx[e][f][dz][dy][qx] -> BB,GB,BG[e][f][dz][qy][qx].  Ends with a barrier.
 // ---------------------------------------------------------------------------
 template<int D1D, int Q1D, int NF>
-__device__ __forceinline__ void grad_xy(const double *B, const double *G, const double *Xs,
-                                        double *Bx, double *Gx, double *BB, double *GB, double *BG,
+__device__ __forceinline__ void grad_xy(const double *B, const double *G, int nel, const double *Xs, int sX,
+                                        double *Bx, double *Gx, int s1, double *BB, double *GB, double *BG, int s2,
                                         int tid, int nthr)
 {
    constexpr int DD = D1D*D1D, QQ = Q1D*Q1D;
-   for (int it = tid; it < NF*DD*Q1D; it += nthr)
+   for (int it = tid; it < nel*NF*DD; it += nthr)         // x pencils (f, dz, dy)
    {
-      const int qx = it % Q1D, r = it / Q1D;    // r = dy + D1D*(dz + D1D*f)
-      double b = 0.0, g = 0.0;
+      const int e = it / (NF*DD), r = it - e*(NF*DD);     // r = dy + D*(dz + D*f)
+      double in[D1D], b[Q1D], g[Q1D];
 #pragma unroll
-      for (int dx = 0; dx < D1D; dx++)
-      {
-         const double x = Xs[dx + D1D*r];
-         b += B[qx + Q1D*dx]*x; g += G[qx + Q1D*dx]*x;
-      }
-      Bx[it] = b; Gx[it] = g;                   // [f][dz][dy][qx]
+      for (int d = 0; d < D1D; d++) { in[d] = Xs[e*sX + d + D1D*r]; }
+      pencil_fwd<D1D,Q1D>(B, in, b);
+      pencil_fwd<D1D,Q1D>(G, in, g);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { Bx[e*s1 + q + Q1D*r] = b[q]; Gx[e*s1 + q + Q1D*r] = g[q]; }
    }
    __syncthreads();
-   for (int it = tid; it < NF*D1D*QQ; it += nthr)
+   for (int it = tid; it < nel*NF*D1D*Q1D; it += nthr)    // y pencils (f, dz, qx)
    {
-      const int qx = it % Q1D, qy = (it / Q1D) % Q1D, r = it / QQ;   // r = dz + D1D*f
-      double bb = 0.0, gb = 0.0, bg = 0.0;
+      const int e = it / (NF*D1D*Q1D), r = it - e*(NF*D1D*Q1D);
+      const int qx = r % Q1D, fz = r / Q1D;               // fz = dz + D*f
+      double xb[D1D], xg[D1D], bb[Q1D], gb[Q1D], bg[Q1D];
 #pragma unroll
-      for (int dy = 0; dy < D1D; dy++)
+      for (int d = 0; d < D1D; d++)
       {
-         const double xb = Bx[qx + Q1D*(dy + D1D*r)], xg = Gx[qx + Q1D*(dy + D1D*r)];
-         const double by = B[qy + Q1D*dy], gy = G[qy + Q1D*dy];
-         bb += by*xb; gb += by*xg; bg += gy*xb;
+         xb[d] = Bx[e*s1 + qx + Q1D*(d + D1D*fz)];
+         xg[d] = Gx[e*s1 + qx + Q1D*(d + D1D*fz)];
       }
-      BB[it] = bb; GB[it] = gb; BG[it] = bg;    // [f][dz][qy][qx]
+      pencil_fwd<D1D,Q1D>(B, xb, bb);
+      pencil_fwd<D1D,Q1D>(B, xg, gb);
+      pencil_fwd<D1D,Q1D>(G, xb, bg);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++)
+      {
+         const int o = e*s2 + qx + Q1D*q + QQ*fz;        // [f][dz][qy][qx]
+         BB[o] = bb[q]; GB[o] = gb[q]; BG[o] = bg[q];
+      }
    }
    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
-// QUpdate
+// QUpdate: one element per CTA, NT threads, one (or more) quadrature points per thread
 // ---------------------------------------------------------------------------
 template<int D1D, int Q1D>
 struct QUpd3DCfg
@@ -155,10 +185,11 @@ struct QUpd3DCfg
    static constexpr int S_ST2 = NF*D1D*QQ;                 // each of BB, GB, BG
    static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
    static constexpr int S_DOF = NF*ND + NL;
-   // dofs alias the stage-2 arrays (dead after stage 1)
+   // dofs alias the stage-2 arrays (dead after the x pencils)
    static constexpr int S_A = (3*S_ST2 > S_DOF) ? 3*S_ST2 : S_DOF;
-   static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + NQ + 32;
-   static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES + sizeof(SmemTables<D1D,Q1D>);
+   static constexpr int S_TAB = 2*Q1D*D1D;                 // B, G for the per-point z pass (runtime qz)
+   static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + NQ + 32 + S_TAB;
+   static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES;
 };
 
 template<int D1D, int Q1D, int NT>
@@ -167,71 +198,43 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
           const int *__restrict__ map, const double *__restrict__ S,
           const double *__restrict__ rho0DetJ0w, const double *__restrict__ Jac0inv,
           const double *__restrict__ gamma, const double *__restrict__ qweights,
+          const double *__restrict__ inv_qweights,
           const QPointParams prm, double *__restrict__ sJit, double *__restrict__ dt_block_min)
 {
    using C = QUpd3DCfg<D1D,Q1D>;
    extern __shared__ double smem[];
-   SmemTables<D1D,Q1D> &T = *reinterpret_cast<SmemTables<D1D,Q1D>*>(smem + C::SMEM_DOUBLES);
    double *A = smem;                            // dofs, later BB | GB | BG
    double *Bx = A + C::S_A, *Gx = Bx + C::S_ST1;
    double *E1 = Gx + C::S_ST1, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2, *red = Eq + C::NQ;
+   double *TB = red + 32, *TG = TB + Q1D*D1D;
    const int tid = threadIdx.x;
    const int e = blockIdx.x;
    const size_t NEQ = (size_t)NE*C::NQ;
-   T.load(tab, tid, NT);
-   // gather x, v (6 scalar fields) and e
+   for (int i = tid; i < Q1D*D1D; i += NT) { TB[i] = tab.B[i]; TG[i] = tab.G[i]; }
+   // gather x, v (6 scalar fields: S = (x | v | e), field f at offset f*ndofs) and e
    {
-      const double *x = S, *en = S + 6*ndofs;
+      const double *en = S + 6*ndofs;
       const int *m = map + (size_t)e*C::ND;
       for (int it = tid; it < C::NF*C::ND; it += NT)
       {
          const int i = it % C::ND, f = it / C::ND;
-         A[it] = x[(size_t)f*ndofs + m[i]];     // S = (x | v | e): field f at offset f*ndofs
+         A[it] = S[(size_t)f*ndofs + __ldg(m + i)];
       }
       for (int it = tid; it < C::NL; it += NT) { A[C::NF*C::ND + it] = en[(size_t)e*C::NL + it]; }
    }
    __syncthreads();
-   // e at quadrature points (uses the dof copy before it is overwritten)
-   l2_values<C::L1D,Q1D>(T.BL, A + C::NF*C::ND, E1, E2, Eq, tid, NT);
-   // stage 1 must finish reading the dofs before stage 2 overwrites A: grad_xy splits the
-   // stages with a barrier, and BB/GB/BG alias A only from stage 2 on.
+   l2_values<C::L1D,Q1D>(tab.BL, 1, A + C::NF*C::ND, 0, E1, 0, E2, 0, Eq, 0, tid, NT);
    double *BB = A, *GB = A + C::S_ST2, *BG = A + 2*C::S_ST2;
-   {
-      constexpr int DD = C::DD, QQ = C::QQ;
-      for (int it = tid; it < C::NF*DD*Q1D; it += NT)
-      {
-         const int qx = it % Q1D, r = it / Q1D;
-         double b = 0.0, g = 0.0;
-#pragma unroll
-         for (int dx = 0; dx < D1D; dx++)
-         {
-            const double xv = A[dx + D1D*r];
-            b += T.B[qx + Q1D*dx]*xv; g += T.G[qx + Q1D*dx]*xv;
-         }
-         Bx[it] = b; Gx[it] = g;
-      }
-      __syncthreads();
-      for (int it = tid; it < C::NF*D1D*QQ; it += NT)
-      {
-         const int qx = it % Q1D, qy = (it / Q1D) % Q1D, r = it / QQ;
-         double bb = 0.0, gb = 0.0, bg = 0.0;
-#pragma unroll
-         for (int dy = 0; dy < D1D; dy++)
-         {
-            const double xb = Bx[qx + Q1D*(dy + D1D*r)], xg = Gx[qx + Q1D*(dy + D1D*r)];
-            const double by = T.B[qy + Q1D*dy], gy = T.G[qy + Q1D*dy];
-            bb += by*xb; gb += by*xg; bg += gy*xb;
-         }
-         BB[it] = bb; GB[it] = gb; BG[it] = bg;
-      }
-      __syncthreads();
-   }
-   // stage 3 + point physics
+   grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, 1, A, 0, Bx, Gx, 0, BB, GB, BG, 0, tid, NT);
+   // z pass + point physics
    const double gam = gamma[e];
    double dt_min = prm.dt_in;
    for (int q = tid; q < C::NQ; q += NT)
    {
       const int col = q % C::QQ, qz = q / C::QQ;
+      double bz[D1D], gz[D1D];
+#pragma unroll
+      for (int dz = 0; dz < D1D; dz++) { bz[dz] = TB[qz + Q1D*dz]; gz[dz] = TG[qz + Q1D*dz]; }
       double J[9], dV[9];
 #pragma unroll
       for (int f = 0; f < 6; f++)
@@ -241,8 +244,7 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
          for (int dz = 0; dz < D1D; dz++)
          {
             const int o = col + C::QQ*(dz + D1D*f);
-            const double bz = T.B[qz + Q1D*dz], gz = T.G[qz + Q1D*dz];
-            g0 += bz*GB[o]; g1 += bz*BG[o]; g2 += gz*BB[o];
+            g0 += bz[dz]*GB[o]; g1 += bz[dz]*BG[o]; g2 += gz[dz]*BB[o];
          }
          if (f < 3) { J[f] = g0; J[f + 3] = g1; J[f + 6] = g2; }
          else { dV[f - 3] = g0; dV[f] = g1; dV[f + 3] = g2; }
@@ -252,40 +254,43 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
       const double *j0 = Jac0inv + eq*9;
 #pragma unroll
       for (int k = 0; k < 9; k++) { J0[k] = __ldg(j0 + k); }
-      const double dtq = qpoint<3>(J, dV, Eq[q], __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q), prm, sJ);
+      const double dtq = qpoint<3>(J, dV, Eq[q], __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q),
+                                   __ldg(inv_qweights + q), prm, sJ);
       dt_min = fmin(dt_min, dtq);
 #pragma unroll
       for (int vd = 0; vd < 3; vd++)
 #pragma unroll
          for (int gd = 0; gd < 3; gd++) { sJit[eq + NEQ*(gd + vd*3)] = sJ[vd + gd*3]; }
    }
-   // block minimum (exact, order independent)
+   // block minimum (exact, order independent); NT is a whole number of warps
    for (int o = 16; o > 0; o >>= 1) { dt_min = fmin(dt_min, __shfl_xor_sync(0xffffffffu, dt_min, o)); }
    if ((tid & 31) == 0) { red[tid >> 5] = dt_min; }
    __syncthreads();
    if (tid == 0)
    {
       double m = red[0];
-      for (int w = 1; w < (NT + 31)/32; w++) { m = fmin(m, red[w]); }
+      for (int w = 1; w < NT/32; w++) { m = fmin(m, red[w]); }
       dt_block_min[blockIdx.x] = m;
    }
 }
 
 // ---------------------------------------------------------------------------
-// Force (L2 -> H1 vector)
+// Force (L2 -> H1 vector), NB elements per CTA
 // ---------------------------------------------------------------------------
 template<int D1D, int Q1D>
 struct Force3DCfg
 {
    static constexpr int L1D = D1D - 1, DD = D1D*D1D, QQ = Q1D*Q1D, ND = D1D*DD, NQ = Q1D*QQ, NL = L1D*L1D*L1D;
-   static constexpr int S_W = 9*D1D*QQ;          // W[c][g][dz][qy][qx]
+   static constexpr int S_W = 9*D1D*QQ;          // W[c][g][dz][qy][qx]; later the element result [c][ND]
    static constexpr int S_V = 3*DD*Q1D;          // each of VA, VB [c][dz][dy][qx]
    static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
-   static constexpr int SMEM_DOUBLES = S_W + 2*S_V + NL + S_E1 + S_E2 + NQ;
-   static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES + sizeof(SmemTables<D1D,Q1D>);
+   // region R1 = W ; region R2 = max(VA|VB, Es|E1|E2|Eq) (the L2 scratch is dead after the z pass)
+   static constexpr int S_L2 = NL + S_E1 + S_E2 + NQ;
+   static constexpr int S_R2 = (2*S_V > S_L2) ? 2*S_V : S_L2;
+   static constexpr int PER_ELEM = S_W + S_R2;
 };
 
-template<int D1D, int Q1D, int NT>
+template<int D1D, int Q1D, int NB, int NT>
 __global__ void __launch_bounds__(NT)
 force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t ndofs,
         const int *__restrict__ map, const double *__restrict__ sJit,
@@ -293,73 +298,92 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
 {
    using C = Force3DCfg<D1D,Q1D>;
    extern __shared__ double smem[];
-   SmemTables<D1D,Q1D> &T = *reinterpret_cast<SmemTables<D1D,Q1D>*>(smem + C::SMEM_DOUBLES);
-   double *W = smem, *VA = W + C::S_W, *VB = VA + C::S_V;
-   double *Es = VB + C::S_V, *E1 = Es + C::NL, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2;
+   constexpr int PE = C::PER_ELEM, QQ = C::QQ, DD = C::DD;
+   double *W = smem;                             // [e][S_W]
+   double *R2 = smem + C::S_W;                   // [e][S_R2], element stride PE for both
+   double *Es = R2, *E1 = Es + C::NL, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2;
+   double *VA = R2, *VB = R2 + C::S_V;
    const int tid = threadIdx.x;
-   const int e = blockIdx.x;
+   const int eb = blockIdx.x*NB;
+   const int nel = min(NB, NE - eb);
    const size_t NEQ = (size_t)NE*C::NQ;
-   constexpr int QQ = C::QQ, DD = C::DD;
-   T.load(tab, tid, NT);
-   for (int it = tid; it < C::NL; it += NT) { Es[it] = x[(size_t)e*C::NL + it]; }
-   __syncthreads();
-   l2_values<C::L1D,Q1D>(T.BL, Es, E1, E2, Eq, tid, NT);
-   // z pass: items (c, g, column): W[c][g][dz][col] = sum_qz Tz(qz,dz) sJit(q,g,c) Eq(q), Tz = G if g == 2
-   for (int it = tid; it < 9*QQ; it += NT)
+   for (int it = tid; it < nel*C::NL; it += NT)
    {
-      const int col = it % QQ, cg = it / QQ;    // cg = g + 3*c
-      const int g = cg % 3;
-      const double *s = sJit + (size_t)e*C::NQ + NEQ*cg + col;
-      double sv[Q1D];
-#pragma unroll
-      for (int qz = 0; qz < Q1D; qz++) { sv[qz] = __ldg(s + QQ*qz)*Eq[col + QQ*qz]; }
-      const double *Tz = (g == 2) ? T.G : T.B;
-#pragma unroll
-      for (int dz = 0; dz < D1D; dz++)
-      {
-         double u = 0.0;
-#pragma unroll
-         for (int qz = 0; qz < Q1D; qz++) { u += Tz[qz + Q1D*dz]*sv[qz]; }
-         W[col + QQ*(dz + D1D*cg)] = u;
-      }
+      const int e = it / C::NL, i = it - e*C::NL;
+      Es[e*PE + i] = x[(size_t)(eb + e)*C::NL + i];
    }
    __syncthreads();
-   // y pass: items (c, dz, dy, qx): VA = By W_c0 (x pass: G), VB = Gy W_c1 + By W_c2 (x pass: B)
-   for (int it = tid; it < 3*DD*Q1D; it += NT)
+   l2_values<C::L1D,Q1D>(tab.BL, nel, Es, PE, E1, PE, E2, PE, Eq, PE, tid, NT);
+   // z pencils (e, c, g, column): W[c][g][dz][col] = sum_qz Tz(qz,dz) sJit(q,g,c) Eq(q), Tz = G for g == 2
+   for (int it = tid; it < nel*9*QQ; it += NT)
    {
-      const int qx = it % Q1D, dy = (it / Q1D) % D1D, dz = (it / (Q1D*D1D)) % D1D, c = it / (Q1D*DD);
-      const double *w0 = W + QQ*(dz + D1D*(0 + 3*c)) + qx;
-      const double *w1 = W + QQ*(dz + D1D*(1 + 3*c)) + qx;
-      const double *w2 = W + QQ*(dz + D1D*(2 + 3*c)) + qx;
-      double va = 0.0, vb = 0.0;
+      const int e = it / (9*QQ), r = it - e*(9*QQ);
+      const int col = r % QQ, cg = r / QQ;      // cg = g + 3*c
+      const double *s = sJit + (size_t)(eb + e)*C::NQ + NEQ*cg + col;
+      double sv[Q1D], w[D1D];
+#pragma unroll
+      for (int qz = 0; qz < Q1D; qz++) { sv[qz] = __ldg(s + QQ*qz); }
+#pragma unroll
+      for (int qz = 0; qz < Q1D; qz++) { sv[qz] *= Eq[e*PE + col + QQ*qz]; }
+      if (cg % 3 == 2) { pencil_bwd<D1D,Q1D>(tab.G, sv, w); }
+      else { pencil_bwd<D1D,Q1D>(tab.B, sv, w); }
+#pragma unroll
+      for (int dz = 0; dz < D1D; dz++) { W[e*PE + col + QQ*(dz + D1D*cg)] = w[dz]; }
+   }
+   __syncthreads();
+   // y pencils (e, c, dz, qx): VA = By W_c0 (x pass: G), VB = Gy W_c1 + By W_c2 (x pass: B)
+   for (int it = tid; it < nel*3*D1D*Q1D; it += NT)
+   {
+      const int e = it / (3*D1D*Q1D), r = it - e*(3*D1D*Q1D);
+      const int qx = r % Q1D, dz = (r / Q1D) % D1D, c = r / (Q1D*D1D);
+      double w0[Q1D], w1[Q1D], w2[Q1D], a[D1D], b1[D1D], b2[D1D];
 #pragma unroll
       for (int qy = 0; qy < Q1D; qy++)
       {
-         const double by = T.B[qy + Q1D*dy], gy = T.G[qy + Q1D*dy];
-         va += by*w0[Q1D*qy];
-         vb += gy*w1[Q1D*qy] + by*w2[Q1D*qy];
+         const int o = e*PE + qx + Q1D*qy + QQ*dz;
+         w0[qy] = W[o + QQ*D1D*(0 + 3*c)]; w1[qy] = W[o + QQ*D1D*(1 + 3*c)]; w2[qy] = W[o + QQ*D1D*(2 + 3*c)];
       }
-      VA[it] = va; VB[it] = vb;                  // [c][dz][dy][qx]
+      pencil_bwd<D1D,Q1D>(tab.B, w0, a);
+      pencil_bwd<D1D,Q1D>(tab.G, w1, b1);
+      pencil_bwd<D1D,Q1D>(tab.B, w2, b2);
+#pragma unroll
+      for (int dy = 0; dy < D1D; dy++)
+      {
+         const int o = e*PE + qx + Q1D*(dy + D1D*(dz + D1D*c));     // [c][dz][dy][qx]
+         VA[o] = a[dy]; VB[o] = b1[dy] + b2[dy];
+      }
    }
    __syncthreads();
-   // x pass + scatter: items (c, dz, dy, dx)
+   // x pencils (e, c, dz, dy): element result [c][ND] parked in W (dead)
    const double eps2 = DBL_EPSILON*DBL_EPSILON;
-   const int *m = map + (size_t)e*C::ND;
-   for (int it = tid; it < 3*C::ND; it += NT)
+   for (int it = tid; it < nel*3*DD; it += NT)
    {
-      const int i = it % C::ND, c = it / C::ND;
-      const int dx = i % D1D, r = i / D1D;       // r = dy + D1D*dz
-      const double *va = VA + Q1D*(r + DD*c), *vb = VB + Q1D*(r + DD*c);
-      double o = 0.0;
+      const int e = it / (3*DD), r = it - e*(3*DD);       // r = dy + D*(dz + D*c)
+      double va[Q1D], vb[Q1D], oa[D1D], ob[D1D];
 #pragma unroll
-      for (int qx = 0; qx < Q1D; qx++) { o += T.G[qx + Q1D*dx]*va[qx] + T.B[qx + Q1D*dx]*vb[qx]; }
-      if (fabs(o) < eps2) { o = 0.0; }            // reference laghos_assembly.cpp:495-512
-      atomicAdd(y + (size_t)c*ndofs + m[i], o);
+      for (int qx = 0; qx < Q1D; qx++) { va[qx] = VA[e*PE + qx + Q1D*r]; vb[qx] = VB[e*PE + qx + Q1D*r]; }
+      pencil_bwd<D1D,Q1D>(tab.G, va, oa);
+      pencil_bwd<D1D,Q1D>(tab.B, vb, ob);
+#pragma unroll
+      for (int dx = 0; dx < D1D; dx++)
+      {
+         double o = oa[dx] + ob[dx];
+         if (fabs(o) < eps2) { o = 0.0; }                 // reference laghos_assembly.cpp:495-512
+         W[e*PE + dx + D1D*r] = o;
+      }
+   }
+   __syncthreads();
+   // scatter-add, lanes along the element-local dof index
+   for (int it = tid; it < nel*3*C::ND; it += NT)
+   {
+      const int e = it / (3*C::ND), r = it - e*(3*C::ND);
+      const int i = r % C::ND, c = r / C::ND;
+      atomicAdd(y + (size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i), W[e*PE + r]);
    }
 }
 
 // ---------------------------------------------------------------------------
-// Force transpose (H1 vector -> L2)
+// Force transpose (H1 vector -> L2), NB elements per CTA
 // ---------------------------------------------------------------------------
 template<int D1D, int Q1D>
 struct ForceT3DCfg
@@ -368,11 +392,13 @@ struct ForceT3DCfg
    static constexpr int NF = 3;
    static constexpr int S_ST1 = NF*DD*Q1D, S_ST2 = NF*D1D*QQ;
    static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
-   static constexpr int SMEM_DOUBLES = NF*ND + 2*S_ST1 + 3*S_ST2 + NQ + S_E1 + S_E2;
-   static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES + sizeof(SmemTables<D1D,Q1D>);
+   // region A: Vs -> BB|GB|BG -> t1 ; region B: Bx|Gx -> t2
+   static constexpr int S_A = (3*S_ST2 > NF*ND) ? 3*S_ST2 : NF*ND;
+   static constexpr int S_B = (2*S_ST1 > S_E2) ? 2*S_ST1 : S_E2;
+   static constexpr int PER_ELEM = S_A + S_B;
 };
 
-template<int D1D, int Q1D, int NT>
+template<int D1D, int Q1D, int NB, int NT>
 __global__ void __launch_bounds__(NT)
 forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t ndofs,
          const int *__restrict__ map, const double *__restrict__ sJit,
@@ -380,82 +406,131 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
 {
    using C = ForceT3DCfg<D1D,Q1D>;
    extern __shared__ double smem[];
-   SmemTables<D1D,Q1D> &T = *reinterpret_cast<SmemTables<D1D,Q1D>*>(smem + C::SMEM_DOUBLES);
-   double *Vs = smem, *Bx = Vs + C::NF*C::ND, *Gx = Bx + C::S_ST1;
-   double *BB = Gx + C::S_ST1, *GB = BB + C::S_ST2, *BG = GB + C::S_ST2;
-   double *QQQ = BG + C::S_ST2, *E1 = QQQ + C::NQ, *E2 = E1 + C::S_E1;
+   constexpr int PE = C::PER_ELEM, QQ = C::QQ;
+   double *RA = smem, *RB = smem + C::S_A;
+   double *Vs = RA, *BB = RA, *GB = RA + C::S_ST2, *BG = RA + 2*C::S_ST2, *t1 = RA;
+   double *Bx = RB, *Gx = RB + C::S_ST1, *t2 = RB;
    const int tid = threadIdx.x;
-   const int e = blockIdx.x;
+   const int eb = blockIdx.x*NB;
+   const int nel = min(NB, NE - eb);
    const size_t NEQ = (size_t)NE*C::NQ;
-   T.load(tab, tid, NT);
+   for (int it = tid; it < nel*C::NF*C::ND; it += NT)
    {
-      const int *m = map + (size_t)e*C::ND;
-      for (int it = tid; it < C::NF*C::ND; it += NT)
-      {
-         const int i = it % C::ND, c = it / C::ND;
-         Vs[it] = v[(size_t)c*ndofs + m[i]];
-      }
+      const int e = it / (C::NF*C::ND), r = it - e*(C::NF*C::ND);
+      const int i = r % C::ND, c = r / C::ND;
+      Vs[e*PE + r] = v[(size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i)];
    }
    __syncthreads();
-   grad_xy<D1D,Q1D,C::NF>(T.B, T.G, Vs, Bx, Gx, BB, GB, BG, tid, NT);
-   for (int q = tid; q < C::NQ; q += NT)
+   grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, nel, Vs, PE, Bx, Gx, PE, BB, GB, BG, PE, tid, NT);
+   // z pencils (e, column): gradients at the Q1D points of the column, contraction with
+   // stressJinvT, then the z pencil of the transposed L2 interpolation in registers
+   for (int it = tid; it < nel*QQ; it += NT)
    {
-      const int col = q % C::QQ, qz = q / C::QQ;
-      const double *s = sJit + (size_t)e*C::NQ + q;
-      double acc = 0.0;
+      const int e = it / QQ, col = it - e*QQ;
+      const double *s = sJit + (size_t)(eb + e)*C::NQ + col;
+      double acc[Q1D];
+#pragma unroll
+      for (int qz = 0; qz < Q1D; qz++) { acc[qz] = 0.0; }
 #pragma unroll
       for (int c = 0; c < 3; c++)
       {
-         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+         double bb[D1D], gb[D1D], bg[D1D], g0[Q1D], g1[Q1D], g2[Q1D];
 #pragma unroll
          for (int dz = 0; dz < D1D; dz++)
          {
-            const int o = col + C::QQ*(dz + D1D*c);
-            const double bz = T.B[qz + Q1D*dz], gz = T.G[qz + Q1D*dz];
-            g0 += bz*GB[o]; g1 += bz*BG[o]; g2 += gz*BB[o];
+            const int o = e*PE + col + QQ*(dz + D1D*c);
+            bb[dz] = BB[o]; gb[dz] = GB[o]; bg[dz] = BG[o];
          }
-         // same association as the reference (:889-899): per component, sum over g, then add
-         const double sc = g0*__ldg(s + NEQ*(0 + 3*c)) + g1*__ldg(s + NEQ*(1 + 3*c)) + g2*__ldg(s + NEQ*(2 + 3*c));
-         acc += sc;
+         pencil_fwd<D1D,Q1D>(tab.B, gb, g0);
+         pencil_fwd<D1D,Q1D>(tab.B, bg, g1);
+         pencil_fwd<D1D,Q1D>(tab.G, bb, g2);
+#pragma unroll
+         for (int qz = 0; qz < Q1D; qz++)
+         {
+            // same association as the reference (:889-899): per component, sum over g, then add
+            const double *sq = s + QQ*qz;
+            acc[qz] += g0[qz]*__ldg(sq + NEQ*(0 + 3*c)) + g1[qz]*__ldg(sq + NEQ*(1 + 3*c)) + g2[qz]*__ldg(sq + NEQ*(2 + 3*c));
+         }
       }
-      QQQ[q] = acc;
+      double o[C::L1D];
+      pencil_bwd<C::L1D,Q1D>(tab.BL, acc, o);
+#pragma unroll
+      for (int lz = 0; lz < C::L1D; lz++) { t2[e*PE + col + QQ*lz] = o[lz]; }   // Bx|Gx are dead
    }
    __syncthreads();
-   l2_values_t<C::L1D,Q1D>(T.BL, QQQ, E2, E1, eout + (size_t)e*C::NL, tid, NT);
+   l2_values_t_yx<C::L1D,Q1D>(tab.BL, nel, t2, PE, t1, PE, eout + (size_t)eb*C::NL, tid, NT);
 }
 
 // ---------------------------------------------------------------------------
-// L2 mass apply: y_e = BL^t D BL x_e (block diagonal)
+// L2 mass apply: y_e = BL^t D BL x_e (block diagonal), NB elements per CTA
 // ---------------------------------------------------------------------------
 template<int D1D, int Q1D>
 struct MassL2Cfg
 {
    static constexpr int L1D = D1D - 1, QQ = Q1D*Q1D, NQ = Q1D*QQ, NL = L1D*L1D*L1D;
    static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
-   static constexpr int PER_ELEM = NL + S_E1 + S_E2 + NQ;
+   static constexpr int PER_ELEM = NL + S_E1 + S_E2;
 };
 
-template<int D1D, int Q1D, int NB, int NTE>   // NB elements per CTA, NTE threads per element
-__global__ void __launch_bounds__(NB*NTE)
+template<int D1D, int Q1D, int NB, int NT>
+__global__ void __launch_bounds__(NT)
 massl2_3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE,
           const double *__restrict__ Dq, const double *__restrict__ x, double *__restrict__ y)
 {
    using C = MassL2Cfg<D1D,Q1D>;
    extern __shared__ double smem[];
-   SmemTables<D1D,Q1D> &T = *reinterpret_cast<SmemTables<D1D,Q1D>*>(smem + NB*C::PER_ELEM);
-   const int el = threadIdx.x / NTE, tid = threadIdx.x % NTE;
-   int e = blockIdx.x*NB + el;
-   const bool active = e < NE;
-   if (!active) { e = NE - 1; }                  // keep barriers uniform; results discarded
-   double *Es = smem + el*C::PER_ELEM, *E1 = Es + C::NL, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2;
-   T.load(tab, threadIdx.x, NB*NTE);
-   for (int it = tid; it < C::NL; it += NTE) { Es[it] = x[(size_t)e*C::NL + it]; }
+   constexpr int PE = C::PER_ELEM, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D;
+   double *Es = smem, *t1 = Es + C::NL, *t2 = t1 + C::S_E1;
+   const int tid = threadIdx.x;
+   const int eb = blockIdx.x*NB;
+   const int nel = min(NB, NE - eb);
+   for (int it = tid; it < nel*C::NL; it += NT)
+   {
+      const int e = it / C::NL, i = it - e*C::NL;
+      Es[e*PE + i] = x[(size_t)(eb + e)*C::NL + i];
+   }
    __syncthreads();
-   l2_values<C::L1D,Q1D>(T.BL, Es, E1, E2, Eq, tid, NTE);
-   for (int q = tid; q < C::NQ; q += NTE) { Eq[q] *= __ldg(Dq + (size_t)e*C::NQ + q); }
+   for (int it = tid; it < nel*LL; it += NT)              // x pencils
+   {
+      const int e = it / LL, r = it - e*LL;
+      double in[L1D], out[Q1D];
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { in[l] = Es[e*PE + l + L1D*r]; }
+      pencil_fwd<L1D,Q1D>(tab.BL, in, out);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { t1[e*PE + q + Q1D*r] = out[q]; }
+   }
    __syncthreads();
-   double *out = active ? y + (size_t)e*C::NL : Es;
-   l2_values_t<C::L1D,Q1D>(T.BL, Eq, E2, E1, out, tid, NTE);
+   for (int it = tid; it < nel*L1D*Q1D; it += NT)         // y pencils
+   {
+      const int e = it / (L1D*Q1D), r = it - e*(L1D*Q1D);
+      const int qx = r % Q1D, lz = r / Q1D;
+      double in[L1D], out[Q1D];
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { in[l] = t1[e*PE + qx + Q1D*(l + L1D*lz)]; }
+      pencil_fwd<L1D,Q1D>(tab.BL, in, out);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { t2[e*PE + qx + Q1D*(q + Q1D*lz)] = out[q]; }
+   }
+   __syncthreads();
+   for (int it = tid; it < nel*QQ; it += NT)              // z pencils: forward, scale by D, back (in place)
+   {
+      const int e = it / QQ, col = it - e*QQ;
+      const double *d = Dq + (size_t)(eb + e)*C::NQ + col;
+      double in[L1D], w[Q1D], u[Q1D], o[L1D];
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { w[q] = __ldg(d + QQ*q); }   // issue the loads first
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { in[l] = t2[e*PE + col + QQ*l]; }
+      pencil_fwd<L1D,Q1D>(tab.BL, in, u);
+#pragma unroll
+      for (int q = 0; q < Q1D; q++) { u[q] *= w[q]; }
+      pencil_bwd<L1D,Q1D>(tab.BL, u, o);
+#pragma unroll
+      for (int l = 0; l < L1D; l++) { t2[e*PE + col + QQ*l] = o[l]; }
+   }
+   __syncthreads();
+   l2_values_t_yx<L1D,Q1D>(tab.BL, nel, t2, PE, t1, PE, y + (size_t)eb*C::NL, tid, NT);
 }
 
 } // namespace tuned

@@ -12,9 +12,11 @@ static int set_smem(K kern, size_t bytes)
    return LAGB_OK;
 }
 
-// <D1D, Q1D, NB1, MINB1, NB3, MINB3, NTQ, NTF>: elements per CTA and minimum resident CTAs
-// for the 1- and 3-component mass apply, threads per element of QUpdate, threads of Force.
-template<int D1D, int Q1D, int NB1, int MINB1, int NB3, int MINB3, int NTQ, int NTF>
+// NTQ and NTF must be multiples of 32 (full-warp shuffles).
+// <D1D, Q1D, NB1, MINB1, NB3, MINB3, NTQ, NBF, NTF>: elements per CTA and minimum resident CTAs
+// for the 1- and 3-component mass apply, threads per element of QUpdate, elements per CTA and
+// threads of Force / Force^T (the L2 mass apply takes 4*NBF elements per 256-thread CTA).
+template<int D1D, int Q1D, int NB1, int MINB1, int NB3, int MINB3, int NTQ, int NBF, int NTF>
 struct TunedLaunch3D
 {
    using Tab = DevTables<D1D,Q1D>;
@@ -37,12 +39,12 @@ struct TunedLaunch3D
    template<int NC, bool WITH_DEN>
    static int mass_launch(Ctx &c, const double *x, double *y)
    {
-      if (NC == 3 && D1D == 4)   // tuning variants of the dominant kernel (lagb_tune_set key 0)
+      if constexpr (NC == 3 && D1D == 4)   // tuning variants of the dominant kernel (lagb_tune_set key 0)
       {
          switch (c.tune[0])
          {
             case 1: return mass_launch_v<NC,WITH_DEN,16,2>(c, x, y);
-            case 2: return mass_launch_v<NC,WITH_DEN,8,4>(c, x, y);
+            case 2: return mass_launch_v<NC,WITH_DEN,8,7>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,32,1>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,8,6>(c, x, y);
          }
@@ -57,13 +59,14 @@ struct TunedLaunch3D
    }
    static int qupdate(Ctx &c, const double *S, const QPointParams &prm)
    {
+      static_assert(NTQ % 32 == 0 && NTF % 32 == 0, "CTA sizes must be whole warps");
       using Cfg = tuned::QUpd3DCfg<D1D,Q1D>;
       auto kern = tuned::qupdate3d<D1D,Q1D,NTQ>;
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
       if (c.NE > c.part_cap) { set_error("qupdate3d: partial buffer too small"); return LAGB_ERR_STATE; }
       kern<<<c.NE, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
-                                                     c.d_gamma, c.d_qweights, prm, c.d_sJit, c.d_part);
+                                                     c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_part);
       LAGB_LAUNCH_CHECK();
       c.dt_nblocks = c.NE;
       return LAGB_OK;
@@ -71,33 +74,34 @@ struct TunedLaunch3D
    static int force_mult(Ctx &c, const double *e, double *v)
    {
       using Cfg = tuned::Force3DCfg<D1D,Q1D>;
-      auto kern = tuned::force3d<D1D,Q1D,NTF>;
+      auto kern = tuned::force3d<D1D,Q1D,NBF,NTF>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NBF*Cfg::PER_ELEM;
       static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
-      kern<<<c.NE, NTF, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
+      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      kern<<<(c.NE + NBF - 1)/NBF, NTF, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
    static int force_mult_t(Ctx &c, const double *v, double *e)
    {
       using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
-      auto kern = tuned::forcet3d<D1D,Q1D,NTF>;
+      auto kern = tuned::forcet3d<D1D,Q1D,NBF,NTF>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NBF*Cfg::PER_ELEM;
       static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
-      kern<<<c.NE, NTF, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
+      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      kern<<<(c.NE + NBF - 1)/NBF, NTF, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
    static int mass_l2(Ctx &c, const double *x, double *y)
    {
       using Cfg = tuned::MassL2Cfg<D1D,Q1D>;
-      constexpr int NTE = (Cfg::NQ >= 256) ? 128 : (Cfg::NQ >= 64 ? 64 : 32);
-      constexpr int NB = 256/NTE;
-      auto kern = tuned::massl2_3d<D1D,Q1D,NB,NTE>;
-      constexpr size_t bytes = sizeof(double)*NB*Cfg::PER_ELEM + sizeof(tuned::SmemTables<D1D,Q1D>);
+      constexpr int NB = 4*NBF, NT = 256;
+      auto kern = tuned::massl2_3d<D1D,Q1D,NB,NT>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
-      kern<<<(c.NE + NB - 1)/NB, NB*NTE, bytes, c.stream>>>(tab(c), c.NE, c.d_massD, x, y);
+      kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.d_massD, x, y);
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
@@ -115,12 +119,12 @@ bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D)
    const int id = (D1D << 4) | Q1D;
    switch (id)
    {
-      //                          D  Q  NB1 MB1 NB3 MB3 NTQ  NTF
-      case 0x22: TunedLaunch3D<2, 2, 64, 1, 32, 1,  32,  64>::install(ks); break;
-      case 0x34: TunedLaunch3D<3, 4, 32, 1, 32, 1,  64, 128>::install(ks); break;
-      case 0x46: TunedLaunch3D<4, 6, 32, 2, 16, 3, 216, 256>::install(ks); break;
-      case 0x58: TunedLaunch3D<5, 8, 16, 1,  8, 1, 256, 256>::install(ks); break;
-      case 0x6A: TunedLaunch3D<6, 10, 8, 1,  4, 1, 256, 256>::install(ks); break;
+      //                          D  Q  NB1 MB1 NB3 MB3 NTQ NBF  NTF
+      case 0x22: TunedLaunch3D<2, 2, 64, 1, 32, 1,  32, 16, 128>::install(ks); break;
+      case 0x34: TunedLaunch3D<3, 4, 32, 1, 32, 1,  64,  8, 256>::install(ks); break;
+      case 0x46: TunedLaunch3D<4, 6, 32, 2, 16, 3, 224,  4, 256>::install(ks); break;
+      case 0x58: TunedLaunch3D<5, 8, 16, 1,  8, 1, 256,  2, 256>::install(ks); break;
+      case 0x6A: TunedLaunch3D<6, 10, 8, 1,  4, 1, 256,  1, 256>::install(ks); break;
       default: return false;
    }
    return true;
