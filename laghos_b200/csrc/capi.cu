@@ -170,12 +170,11 @@ int halo_sum(Ctx &c, double *v, int nc)
    return LAGB_OK;
 }
 
-__global__ void build_dinvm(int64_t n, int dim, const double *__restrict__ diag, double *__restrict__ dinvm)
+__global__ void build_dinv(int64_t n, const double *__restrict__ diag, double *__restrict__ dinv)
 {
    for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
    {
-      const double v = 1.0/diag[i];
-      for (int c = 0; c < dim; c++) { dinvm[i + c*n] = v; }
+      dinv[i] = 1.0/diag[i];
    }
 }
 __global__ void neg_inplace(double *y, int64_t n)
@@ -207,7 +206,8 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    const int64_t n = l2 ? c.ndofs_l2 : c.ndofs;
    const int64_t cs = n;
    double *r = l2 ? c.d_lr : c.d_r, *d = l2 ? c.d_ld : c.d_d, *z = l2 ? c.d_lz : c.d_z;
-   const double *dinvm = l2 ? nullptr : c.d_dinvm + (size_t)comp0*c.ndofs;
+   pcg::Prec P;
+   P.dinv = l2 ? nullptr : c.d_dinv; P.ess = l2 ? nullptr : c.d_essmask; P.comp0 = comp0;
    const unsigned char *own = l2 ? nullptr : c.d_own;
    const int g = vec_grid(n);
    if (g*NC > c.part_cap) { set_error("pcg: partial buffer too small"); return LAGB_ERR_STATE; }
@@ -225,20 +225,31 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       if (want_den && ks.tuned_mass) { den_blocks = c.dt_nblocks; }
       return halo_sum(c, z, NC);
    };
+   // per-block partials -> (sum over ranks) -> what the finish kernels read.
+   // Single rank: the finish kernel reduces the partials itself (fixed order).
+   // Multi rank: reduce to NC sums, NCCL all-reduce in-stream, finish reads the NC sums.
+   auto reduced = [&](int nblocks, double *tmp, const double *&src, int &nsrc) -> int
+   {
+      if (c.nranks <= 1) { src = c.d_part; nsrc = nblocks; return LAGB_OK; }
+      pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(nblocks, c.d_part, tmp);
+      LAGB_LAUNCH_CHECK();
+      int rc = allreduce_sum(c, tmp, NC); if (rc) { return rc; }
+      src = tmp; nsrc = 1;
+      return LAGB_OK;
+   };
 
-   int rc, den_blocks = 0;
+   int rc, den_blocks = 0, nsrc = 0;
+   const double *src = nullptr;
    if (iterative_mode)
    {
       if (!l2) { LAGB_CUDA(cudaMemsetAsync(z, 0, sizeof(double)*NC*n, c.stream)); }
       rc = apply(x, false, den_blocks); if (rc) { return rc; }
    }
    else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
-   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, dinvm, own, r, d, c.d_part, iterative_mode ? 1 : 0);
+   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, P, own, r, d, c.d_part, iterative_mode ? 1 : 0);
    LAGB_LAUNCH_CHECK();
-   pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(g, c.d_part, c.d_tmp);
-   LAGB_LAUNCH_CHECK();
-   rc = allreduce_sum(c, c.d_tmp, NC); if (rc) { return rc; }
-   pcg::finish_init<NC><<<1, 32, 0, c.stream>>>(c.d_state, c.d_tmp, rel_tol, 0.0);
+   rc = reduced(g, c.d_tmp, src, nsrc); if (rc) { return rc; }
+   pcg::finish_init<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, rel_tol, 0.0);
    LAGB_LAUNCH_CHECK();
 
    // The host only needs to know when every component has stopped; iterations are
@@ -265,19 +276,15 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
          LAGB_LAUNCH_CHECK();
          den_blocks = g;
       }
-      pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(den_blocks, c.d_part, c.d_tmp);
+      rc = reduced(den_blocks, c.d_tmp, src, nsrc); if (rc) { return rc; }
+      pcg::finish_den<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it);
       LAGB_LAUNCH_CHECK();
-      rc = allreduce_sum(c, c.d_tmp, NC); if (rc) { return rc; }
-      pcg::finish_den<NC><<<1, 32, 0, c.stream>>>(c.d_state, c.d_tmp, it);
+      pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, d, z, P, own, c.d_part);
       LAGB_LAUNCH_CHECK();
-      pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, d, z, dinvm, own, c.d_part);
+      rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
+      pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
       LAGB_LAUNCH_CHECK();
-      pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(g, c.d_part, c.d_tmp + 4);
-      LAGB_LAUNCH_CHECK();
-      rc = allreduce_sum(c, c.d_tmp + 4, NC); if (rc) { return rc; }
-      pcg::finish_beta<NC><<<1, 32, 0, c.stream>>>(c.d_state, c.d_tmp + 4, it, max_iter);
-      LAGB_LAUNCH_CHECK();
-      pcg::update_d<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, d, r, dinvm, z);
+      pcg::update_d<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, d, r, P, z);
       LAGB_LAUNCH_CHECK();
       if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
    }
@@ -353,7 +360,13 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    rc |= dev_upload(&c.d_gamma, d->h_gamma, (size_t)c.NE);
    rc |= dev_alloc(&c.d_sJit, NEQ*D2); rc |= dev_alloc(&c.d_rho0DetJ0w, NEQ);
    rc |= dev_alloc(&c.d_Jac0inv, NEQ*D2); rc |= dev_alloc(&c.d_massD, NEQ);
-   rc |= dev_alloc(&c.d_diag, (size_t)c.ndofs); rc |= dev_alloc(&c.d_dinvm, (size_t)c.ndofs*c.dim);
+   rc |= dev_alloc(&c.d_diag, (size_t)c.ndofs); rc |= dev_alloc(&c.d_dinv, (size_t)c.ndofs);
+   {
+      // bit c of essmask[i]: scalar dof i is essential for velocity component c
+      std::vector<unsigned char> em((size_t)c.ndofs, 0);
+      for (int k = 0; k < c.dim; k++) { for (int j = 0; j < d->ness[k]; j++) { em[d->h_ess[k][j]] |= (unsigned char)(1u << k); } }
+      rc |= dev_upload(&c.d_essmask, em.data(), em.size());
+   }
    rc |= dev_alloc(&c.d_r, (size_t)c.ndofs*c.dim); rc |= dev_alloc(&c.d_d, (size_t)c.ndofs*c.dim);
    rc |= dev_alloc(&c.d_z, (size_t)c.ndofs*c.dim);
    rc |= dev_alloc(&c.d_lr, (size_t)c.ndofs_l2); rc |= dev_alloc(&c.d_ld, (size_t)c.ndofs_l2);
@@ -376,7 +389,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    Ctx &c = h->c;
    cudaStreamSynchronize(c.stream);
    void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_inv_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
-                   c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinvm, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
+                   c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinv, c.d_essmask, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
                    c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
@@ -420,14 +433,8 @@ int lagb_setup_qdata0(lagb_ctx *h, const double *d_x0, const double *d_rho0_gf, 
    LAGB_CUDA(cudaMemsetAsync(c.d_diag, 0, sizeof(double)*c.ndofs, c.stream));
    rc = ks.mass_diag(c, c.d_diag); if (rc) { return rc; }
    rc = halo_sum(c, c.d_diag, 1); if (rc) { return rc; }
-   build_dinvm<<<vec_grid(c.ndofs), pcg::RB, 0, c.stream>>>(c.ndofs, c.dim, c.d_diag, c.d_dinvm);
+   build_dinv<<<vec_grid(c.ndofs), pcg::RB, 0, c.stream>>>(c.ndofs, c.d_diag, c.d_dinv);
    LAGB_LAUNCH_CHECK();
-   for (int k = 0; k < c.dim; k++)
-   {
-      if (c.ness[k] == 0) { continue; }
-      pcg::vec_zero_idx<<<std::max(1, std::min(1024, (c.ness[k] + 255)/256)), 256, 0, c.stream>>>(c.d_dinvm + (size_t)k*c.ndofs, c.d_ess[k], c.ness[k]);
-      LAGB_LAUNCH_CHECK();
-   }
    LAGB_CUDA(cudaStreamSynchronize(c.stream));
    c.setup_done = true;
    if (h0_out) { *h0_out = c.h0; }

@@ -56,7 +56,8 @@ struct Ctx
    int *d_map = nullptr; int *d_ess[3] = {nullptr, nullptr, nullptr}; int ness[3] = {0, 0, 0};
    double *d_qweights = nullptr, *d_inv_qweights = nullptr, *d_gamma = nullptr;
    double *d_sJit = nullptr, *d_rho0DetJ0w = nullptr, *d_Jac0inv = nullptr, *d_massD = nullptr;
-   double *d_diag = nullptr, *d_dinvm = nullptr;     // [ndofs], [dim*ndofs] (masked)
+   double *d_diag = nullptr, *d_dinv = nullptr;      // [ndofs] mass diagonal and its inverse
+   unsigned char *d_essmask = nullptr;               // [ndofs] bit c: essential for component c
    double *d_r = nullptr, *d_d = nullptr, *d_z = nullptr;      // [dim*ndofs]
    double *d_lr = nullptr, *d_ld = nullptr, *d_lz = nullptr;   // [ndofs_l2]
    double *d_part = nullptr; int part_cap = 0;                 // reduction partials

@@ -76,16 +76,37 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
    // ---- phase 0: cooperative gather, lanes along the element-local dof index (runs of D1D
    //      contiguous L-vector entries per lattice row).  Slice (c,e,dz) is parked in the
    //      first DD slots of its own plane.
-   for (int it = t; it < nel*C::ND; it += C::T)
    {
-      const int e2 = it / C::ND, i = it - e2*C::ND;
-      const int id = __ldg(map + (size_t)eb*C::ND + it);
-      sIdx[it] = id;
-      const int z = i / C::DD, ixy = i - z*C::DD;
+      // all index loads first, then all value loads (independent requests in flight), then the stores
+      constexpr int NIT = (NB*C::ND + C::T - 1)/C::T;
+      const int nd = nel*C::ND;
+      int id[NIT];
 #pragma unroll
-      for (int cc = 0; cc < NC; cc++)
+      for (int k = 0; k < NIT; k++)
       {
-         sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy] = x[(size_t)cc*cstride + id];
+         const int it = t + k*C::T;
+         id[k] = (it < nd) ? __ldg(map + (size_t)eb*C::ND + it) : 0;
+      }
+      double xv[NIT][NC];
+#pragma unroll
+      for (int k = 0; k < NIT; k++)
+      {
+         const int it = t + k*C::T;
+#pragma unroll
+         for (int cc = 0; cc < NC; cc++) { xv[k][cc] = (it < nd) ? x[(size_t)cc*cstride + id[k]] : 0.0; }
+      }
+#pragma unroll
+      for (int k = 0; k < NIT; k++)
+      {
+         const int it = t + k*C::T;
+         if (it < nd)
+         {
+            const int e2 = it / C::ND, i = it - e2*C::ND;
+            const int z = i / C::DD, ixy = i - z*C::DD;
+            sIdx[it] = id[k];
+#pragma unroll
+            for (int cc = 0; cc < NC; cc++) { sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy] = xv[k][cc]; }
+         }
       }
    }
    __syncthreads();

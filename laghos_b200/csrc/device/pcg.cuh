@@ -29,6 +29,22 @@ struct State                  // lives in device memory
    int all_done;
 };
 
+// Jacobi preconditioner with the essential dofs of component `comp` eliminated: one shared
+// inverse diagonal for all components plus a per-dof bit mask (bit c = essential for
+// component c) instead of `dim` masked copies of the diagonal (saves 2 vector reads per pass).
+struct Prec
+{
+   const double *dinv;            // [n] or nullptr (unpreconditioned L2 CG)
+   const unsigned char *ess;      // [n] or nullptr
+   int comp0;                     // component of the first system
+};
+__device__ __forceinline__ double prec_apply(const Prec &P, int64_t i, int c, double r)
+{
+   if (!P.dinv) { return r; }
+   const double z = P.dinv[i]*r;
+   return (P.ess && ((P.ess[i] >> (P.comp0 + c)) & 1)) ? 0.0 : z;
+}
+
 __device__ __forceinline__ double block_sum(double v, double *sh)
 {
    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
@@ -44,7 +60,7 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
 // r = b - z (z = A x), zz = dinvm*r, d = zz, nom_part = sum own*zz*r ; z = 0
 template<int NC>
 __global__ void init_residual(int64_t n, int64_t cstride, const double *__restrict__ b, double *__restrict__ z,
-                              const double *__restrict__ dinvm, const unsigned char *__restrict__ own,
+                              const Prec P, const unsigned char *__restrict__ own,
                               double *__restrict__ r, double *__restrict__ d, double *__restrict__ part,
                               int iterative_mode)
 {
@@ -60,7 +76,7 @@ __global__ void init_residual(int64_t n, int64_t cstride, const double *__restri
       {
          const int64_t k = i + c*cstride;
          const double rr = iterative_mode ? b[k] - z[k] : b[k];
-         const double zz = dinvm ? dinvm[k]*rr : rr;
+         const double zz = prec_apply(P, i, c, rr);
          r[k] = rr; d[k] = zz; z[k] = 0.0;
          acc[c] += w*zz*rr;
       }
@@ -111,11 +127,37 @@ __global__ void reduce_partials(int nblocks, const double *__restrict__ part, do
    }
 }
 
-// after the initial nom reduction (and allreduce): st.nom holds the sum in `tmp`
+// Fixed-order reduction of part[b*NC + c], b < nblocks, by one block of FB threads: thread t
+// sums b = t, t+FB, ... (4 independent partial sums keep the loads in flight), then a
+// shuffle/shared tree.  Result valid on thread 0.
+constexpr int FB = 512;
 template<int NC>
-__global__ void finish_init(State *st, const double *tmp, double rel_tol, double abs_tol)
+__device__ __forceinline__ void reduce_to_thread0(const double *__restrict__ part, int nblocks, double *out, double *sh)
 {
-   if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+   {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int b = threadIdx.x;
+      for (; b + 3*FB < nblocks; b += 4*FB)
+      {
+         a0 += part[(size_t)b*NC + c]; a1 += part[(size_t)(b + FB)*NC + c];
+         a2 += part[(size_t)(b + 2*FB)*NC + c]; a3 += part[(size_t)(b + 3*FB)*NC + c];
+      }
+      for (; b < nblocks; b += FB) { a0 += part[(size_t)b*NC + c]; }
+      out[c] = block_sum((a0 + a1) + (a2 + a3), sh);
+   }
+}
+
+// The finish kernels take the per-block partials straight from the producing kernel
+// (nblocks > 1, single rank) or the already reduced and all-reduced sums (nblocks == 1).
+template<int NC>
+__global__ void finish_init(State *st, const double *part, int nblocks, double rel_tol, double abs_tol)
+{
+   __shared__ double sh[32];
+   double tmp[NC];
+   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (threadIdx.x != 0) { return; }
    int all = 1;
    for (int c = 0; c < NC; c++)
    {
@@ -134,9 +176,12 @@ __global__ void finish_init(State *st, const double *tmp, double rel_tol, double
 
 // den reduced into tmp: alpha = nom/den
 template<int NC>
-__global__ void finish_den(State *st, const double *tmp, int iter)
+__global__ void finish_den(State *st, const double *part, int nblocks, int iter)
 {
-   if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+   __shared__ double sh[32];
+   double tmp[NC];
+   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (threadIdx.x != 0) { return; }
    for (int c = 0; c < NC; c++)
    {
       if (st->done[c]) { continue; }
@@ -156,7 +201,7 @@ __global__ void finish_den(State *st, const double *tmp, int iter)
 template<int NC>
 __global__ void update_xr(int64_t n, int64_t cstride, const State *__restrict__ st,
                           double *__restrict__ x, double *__restrict__ r, const double *__restrict__ d,
-                          const double *__restrict__ z, const double *__restrict__ dinvm,
+                          const double *__restrict__ z, const Prec P,
                           const unsigned char *__restrict__ own, double *__restrict__ part)
 {
    __shared__ double sh[32];
@@ -174,7 +219,7 @@ __global__ void update_xr(int64_t n, int64_t cstride, const State *__restrict__ 
          x[k] = x[k] + alpha[c]*d[k];
          const double rr = r[k] - alpha[c]*z[k];
          r[k] = rr;
-         const double zz = dinvm ? dinvm[k]*rr : rr;
+         const double zz = prec_apply(P, i, c, rr);
          acc[c] += w*rr*zz;
       }
    }
@@ -188,9 +233,12 @@ __global__ void update_xr(int64_t n, int64_t cstride, const State *__restrict__ 
 
 // betanom reduced into tmp: convergence test, beta, nom <- betanom
 template<int NC>
-__global__ void finish_beta(State *st, const double *tmp, int iter, int max_iter)
+__global__ void finish_beta(State *st, const double *part, int nblocks, int iter, int max_iter)
 {
-   if (threadIdx.x != 0 || blockIdx.x != 0) { return; }
+   __shared__ double sh[32];
+   double tmp[NC];
+   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (threadIdx.x != 0) { return; }
    int all = 1;
    for (int c = 0; c < NC; c++)
    {
@@ -215,7 +263,7 @@ __global__ void finish_beta(State *st, const double *tmp, int iter, int max_iter
 template<int NC>
 __global__ void update_d(int64_t n, int64_t cstride, const State *__restrict__ st,
                          double *__restrict__ d, const double *__restrict__ r,
-                         const double *__restrict__ dinvm, double *__restrict__ z)
+                         const Prec P, double *__restrict__ z)
 {
    double beta[NC]; bool skip[NC];
 #pragma unroll
@@ -228,7 +276,7 @@ __global__ void update_d(int64_t n, int64_t cstride, const State *__restrict__ s
          const int64_t k = i + c*cstride;
          if (!skip[c])
          {
-            const double zz = dinvm ? dinvm[k]*r[k] : r[k];
+            const double zz = prec_apply(P, i, c, r[k]);
             d[k] = zz + beta[c]*d[k];
          }
          z[k] = 0.0;

@@ -1,5 +1,6 @@
 // Launchers for the tuned 3D kernels (sm_100a).
 #include "ctx.hpp"
+#include <algorithm>
 #include "device/mass3d.cuh"
 #include "device/staged3d.cuh"
 
@@ -57,41 +58,93 @@ struct TunedLaunch3D
       if (nc == 1) { return with_den ? mass_launch<1,true>(c, x, y) : mass_launch<1,false>(c, x, y); }
       set_error("mass3d: nc must be 1 or 3"); return LAGB_ERR_INVALID;
    }
-   static int qupdate(Ctx &c, const double *S, const QPointParams &prm)
+   template<int MINB>
+   static int qupdate_launch(Ctx &c, const double *S, const QPointParams &prm)
    {
       static_assert(NTQ % 32 == 0 && NTF % 32 == 0, "CTA sizes must be whole warps");
       using Cfg = tuned::QUpd3DCfg<D1D,Q1D>;
-      auto kern = tuned::qupdate3d<D1D,Q1D,NTQ>;
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
-      if (c.NE > c.part_cap) { set_error("qupdate3d: partial buffer too small"); return LAGB_ERR_STATE; }
-      kern<<<c.NE, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
-                                                     c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_part);
+      auto kern = tuned::qupdate3d<D1D,Q1D,NTQ,MINB>;
+      static int resident = 0;
+      if (!resident)
+      {
+         int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; }
+         int per_sm = 0, nsm = 0;
+         LAGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTQ, Cfg::SMEM_BYTES));
+         LAGB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
+         resident = std::max(1, per_sm)*nsm;   // persistent: one CTA per resident slot
+      }
+      const int grid = std::min(c.NE, resident);
+      if (grid > c.part_cap) { set_error("qupdate3d: partial buffer too small"); return LAGB_ERR_STATE; }
+      kern<<<grid, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
+                                                    c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_part);
       LAGB_LAUNCH_CHECK();
-      c.dt_nblocks = c.NE;
+      c.dt_nblocks = grid;
+      return LAGB_OK;
+   }
+   static int qupdate(Ctx &c, const double *S, const QPointParams &prm)
+   {
+      if constexpr (NTQ <= 224)   // tuning variants (lagb_tune_set key 2): resident CTAs per SM
+      {
+         switch (c.tune[2])
+         {
+            case 1: return qupdate_launch<3>(c, S, prm);
+            case 2: return qupdate_launch<1>(c, S, prm);
+         }
+         return qupdate_launch<2>(c, S, prm);
+      }
+      return qupdate_launch<1>(c, S, prm);
+   }
+   template<int NB, int NT>
+   static int force_launch(Ctx &c, const double *e, double *v)
+   {
+      using Cfg = tuned::Force3DCfg<D1D,Q1D>;
+      auto kern = tuned::force3d<D1D,Q1D,NB,NT>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
+   template<int NB, int NT>
+   static int forcet_launch(Ctx &c, const double *v, double *e)
+   {
+      using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
+      auto kern = tuned::forcet3d<D1D,Q1D,NB,NT>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
+      LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
    static int force_mult(Ctx &c, const double *e, double *v)
    {
-      using Cfg = tuned::Force3DCfg<D1D,Q1D>;
-      auto kern = tuned::force3d<D1D,Q1D,NBF,NTF>;
-      constexpr size_t bytes = sizeof(double)*(size_t)NBF*Cfg::PER_ELEM;
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
-      kern<<<(c.NE + NBF - 1)/NBF, NTF, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
-      LAGB_LAUNCH_CHECK();
-      return LAGB_OK;
+      if constexpr (D1D == 4)   // tuning variants (lagb_tune_set key 1)
+      {
+         switch (c.tune[1])
+         {
+            case 1: return force_launch<2,128>(c, e, v);
+            case 2: return force_launch<1,64>(c, e, v);
+            case 3: return force_launch<2,256>(c, e, v);
+            case 4: return force_launch<1,128>(c, e, v);
+         }
+      }
+      return force_launch<NBF,NTF>(c, e, v);
    }
    static int force_mult_t(Ctx &c, const double *v, double *e)
    {
-      using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
-      auto kern = tuned::forcet3d<D1D,Q1D,NBF,NTF>;
-      constexpr size_t bytes = sizeof(double)*(size_t)NBF*Cfg::PER_ELEM;
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
-      kern<<<(c.NE + NBF - 1)/NBF, NTF, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
-      LAGB_LAUNCH_CHECK();
-      return LAGB_OK;
+      if constexpr (D1D == 4)
+      {
+         switch (c.tune[1])
+         {
+            case 1: return forcet_launch<2,128>(c, v, e);
+            case 2: return forcet_launch<1,64>(c, v, e);
+            case 3: return forcet_launch<2,256>(c, v, e);
+            case 4: return forcet_launch<1,128>(c, v, e);
+         }
+      }
+      return forcet_launch<NBF,NTF>(c, v, e);
    }
    static int mass_l2(Ctx &c, const double *x, double *y)
    {

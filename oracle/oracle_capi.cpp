@@ -2,6 +2,7 @@
 // ctypes-facing C API of the oracle: used only by tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs.
 #include "laghos_oracle.hpp"
+#include "../laghos_b200/csrc/host/partition.hpp"
 
 struct OrcHandle
 {
@@ -29,6 +30,26 @@ void *orc_create(const char *mesh, int rs, int problem, int ok, int ot, int oq, 
       return h;
    }
    catch (const std::exception &e) { fprintf(stderr, "orc_create: %s\n", e.what()); return nullptr; }
+}
+// one rank's element box of a Cartesian partition (tests of the multi-rank host logic)
+void *orc_create_part(const char *mesh, int rs, int problem, int ok, int ot, int oq, double blast_scale,
+                      int impose_visc, double cfl, double cgt, int cgm, int nthreads, int rank, const int *pgrid)
+{
+   try
+   {
+      std::vector<double> coarse[3]; int dim = 0;
+      if (!lagb::named_coarse_mesh(mesh, dim, coarse)) { return nullptr; }
+      lagb::RectMesh rm; rm.build(dim, coarse, rs);
+      lagb::ProblemSpec sp;
+      sp.problem = problem; sp.dim = dim; sp.ok = ok; sp.ot = ot; sp.oq = oq;
+      sp.blast_scale = blast_scale; sp.impose_visc = impose_visc != 0;
+      lagb::Partition part; part.build(dim, rm.n, pgrid, rank, ok);
+      OrcHandle *h = new OrcHandle();
+      h->P.build(sp, rm, part.lo, part.hi);
+      h->H = new oracle::Hydro(h->P, cfl, cgt, cgm, nthreads);
+      return h;
+   }
+   catch (const std::exception &e) { fprintf(stderr, "orc_create_part: %s\n", e.what()); return nullptr; }
 }
 void orc_destroy(void *h) { delete (OrcHandle*)h; }
 

@@ -22,6 +22,9 @@ def load():
         lib.orc_create.restype = C.c_void_p
         lib.orc_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                    C.c_double, C.c_double, C.c_int, C.c_int]
+        lib.orc_create_part.restype = C.c_void_p
+        lib.orc_create_part.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                        C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int * 3)]
         lib.orc_destroy.argtypes = [C.c_void_p]
         lib.orc_info.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         lib.orc_get_S0.argtypes = [C.c_void_p, dp]
@@ -58,12 +61,17 @@ def _dim(mesh):
 
 class Oracle:
     def __init__(self, mesh="cube01_hex", rs=0, problem=1, ok=2, ot=1, oq=-1, blast_scale=None, impose_visc=False,
-                 cfl=0.5, cg_tol=1e-8, cg_max_iter=300, nthreads=1):
+                 cfl=0.5, cg_tol=1e-8, cg_max_iter=300, nthreads=1, rank=0, pgrid=None):
         self.lib = load()
         if blast_scale is None:
             blast_scale = 1.0 / 2 ** _dim(mesh)
-        self.h = self.lib.orc_create(mesh.encode(), rs, problem, ok, ot, oq, blast_scale, int(impose_visc),
-                                     cfl, cg_tol, cg_max_iter, nthreads)
+        if pgrid is None:
+            self.h = self.lib.orc_create(mesh.encode(), rs, problem, ok, ot, oq, blast_scale, int(impose_visc),
+                                         cfl, cg_tol, cg_max_iter, nthreads)
+        else:
+            pg = (C.c_int * 3)(*pgrid)
+            self.h = self.lib.orc_create_part(mesh.encode(), rs, problem, ok, ot, oq, blast_scale, int(impose_visc),
+                                              cfl, cg_tol, cg_max_iter, nthreads, rank, C.byref(pg))
         if not self.h:
             raise RuntimeError("orc_create failed")
         info = (C.c_longlong * 10)()

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--problem", type=int, default=1)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--mass-variants", default="0,1,2,3,4")
+    ap.add_argument("--force-variants", default="0,1,2,3,4")
+    ap.add_argument("--q-variants", default="0,1,2")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -67,13 +69,19 @@ def main():
         print(f"{name:34s} {us:10.1f} us  {gbytes:7.3f} GB  {bw:8.1f} GB/s  {100 * bw / peak:5.1f}% of {peak:.0f}", flush=True)
 
     dim = P.dim
-    report("qupdate (fused)", timeit(lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
-           8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)))
-    report("force_mult", timeit(lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
-           8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+    for var in [int(s) for s in args.q_variants.split(",")]:
+        c.tune(2, var)
+        report(f"qupdate (fused) variant {var}", timeit(lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
+               8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)))
+    c.tune(2, 0)
     ye = c.empty(nl)
-    report("force_mult_transpose", timeit(lambda: c.lib.lagb_force_mult_transpose(c.h, c._p(v), c._p(ye))),
-           8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+    for var in [int(s) for s in args.force_variants.split(",")]:
+        c.tune(1, var)
+        report(f"force_mult variant {var}", timeit(lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
+               8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+        report(f"force_mult_transpose variant {var}", timeit(lambda: c.lib.lagb_force_mult_transpose(c.h, c._p(v), c._p(ye))),
+               8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+    c.tune(1, 0)
     y1 = c.empty(nd)
     report("vmass_mult (1 comp)", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
            8e-9 * (NE * NQ + 2 * nd))
