@@ -174,7 +174,7 @@ __device__ __forceinline__ void grad_xy(const double *B, const double *G, int ne
 }
 
 // ---------------------------------------------------------------------------
-// QUpdate: one element at a time per CTA, NT threads, one (or more) quadrature points per thread
+// QUpdate: one element per CTA, NT threads, one (or more) quadrature points per thread
 // ---------------------------------------------------------------------------
 template<int D1D, int Q1D>
 struct QUpd3DCfg
@@ -192,9 +192,6 @@ struct QUpd3DCfg
    static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES;
 };
 
-// Persistent CTAs (grid = resident CTAs), one element per iteration.  The gather of the NEXT
-// element (restriction indices two elements ahead, dof values one element ahead) is in
-// flight while the current element's ~1300 fp64 instructions per point execute.
 template<int D1D, int Q1D, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t ndofs,
@@ -211,91 +208,59 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
    double *E1 = Gx + C::S_ST1, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2, *red = Eq + C::NQ;
    double *TB = red + 32, *TG = TB + Q1D*D1D;
    const int tid = threadIdx.x;
+   const int e = blockIdx.x;
    const size_t NEQ = (size_t)NE*C::NQ;
    for (int i = tid; i < Q1D*D1D; i += NT) { TB[i] = tab.B[i]; TG[i] = tab.G[i]; }
-   // gather items: it < NF*ND: field f = it/ND of S = (x | v | e) at map[e*ND + it%ND];
-   //               else the element's L2 energy dofs (no indirection)
-   constexpr int NITEMS = C::NF*C::ND + C::NL, NIT = (NITEMS + NT - 1)/NT;
-   const double *en = S + 6*ndofs;
-   auto load_idx = [&](int e, int (&idx)[NIT])
+   // gather x, v (6 scalar fields: S = (x | v | e), field f at offset f*ndofs) and e
    {
-#pragma unroll
-      for (int k = 0; k < NIT; k++)
+      const double *en = S + 6*ndofs;
+      const int *m = map + (size_t)e*C::ND;
+      for (int it = tid; it < C::NF*C::ND; it += NT)
       {
-         const int it = tid + k*NT;
-         idx[k] = (e < NE && it < C::NF*C::ND) ? __ldg(map + (size_t)e*C::ND + it % C::ND) : 0;
+         const int i = it % C::ND, f = it / C::ND;
+         A[it] = S[(size_t)f*ndofs + __ldg(m + i)];
       }
-   };
-   auto load_val = [&](int e, const int (&idx)[NIT], double (&val)[NIT])
-   {
-#pragma unroll
-      for (int k = 0; k < NIT; k++)
-      {
-         const int it = tid + k*NT;
-         val[k] = 0.0;
-         if (e < NE)
-         {
-            if (it < C::NF*C::ND) { val[k] = S[(size_t)(it / C::ND)*ndofs + idx[k]]; }
-            else if (it < NITEMS) { val[k] = en[(size_t)e*C::NL + (it - C::NF*C::ND)]; }
-         }
-      }
-   };
-   int idx_next[NIT]; double val_cur[NIT];
-   {
-      int idx0[NIT];
-      load_idx(blockIdx.x, idx0);
-      load_val(blockIdx.x, idx0, val_cur);
-      load_idx(blockIdx.x + gridDim.x, idx_next);
+      for (int it = tid; it < C::NL; it += NT) { A[C::NF*C::ND + it] = en[(size_t)e*C::NL + it]; }
    }
-   double dt_min = prm.dt_in;
+   __syncthreads();
+   l2_values<C::L1D,Q1D>(tab.BL, 1, A + C::NF*C::ND, 0, E1, 0, E2, 0, Eq, 0, tid, NT);
    double *BB = A, *GB = A + C::S_ST2, *BG = A + 2*C::S_ST2;
-   for (int e = blockIdx.x; e < NE; e += gridDim.x)
+   grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, 1, A, 0, Bx, Gx, 0, BB, GB, BG, 0, tid, NT);
+   // z pass + point physics
+   const double gam = gamma[e];
+   double dt_min = prm.dt_in;
+   for (int q = tid; q < C::NQ; q += NT)
    {
+      const int col = q % C::QQ, qz = q / C::QQ;
+      double bz[D1D], gz[D1D];
 #pragma unroll
-      for (int k = 0; k < NIT; k++) { const int it = tid + k*NT; if (it < NITEMS) { A[it] = val_cur[k]; } }
-      __syncthreads();
-      // prefetch: values of the next element (its indices arrived during the previous
-      // iteration), indices of the one after
-      load_val(e + gridDim.x, idx_next, val_cur);
-      load_idx(e + 2*gridDim.x, idx_next);
-      l2_values<C::L1D,Q1D>(tab.BL, 1, A + C::NF*C::ND, 0, E1, 0, E2, 0, Eq, 0, tid, NT);
-      grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, 1, A, 0, Bx, Gx, 0, BB, GB, BG, 0, tid, NT);
-      // z pass + point physics
-      const double gam = __ldg(gamma + e);
-      for (int q = tid; q < C::NQ; q += NT)
+      for (int dz = 0; dz < D1D; dz++) { bz[dz] = TB[qz + Q1D*dz]; gz[dz] = TG[qz + Q1D*dz]; }
+      double J[9], dV[9];
+#pragma unroll
+      for (int f = 0; f < 6; f++)
       {
-         const int col = q % C::QQ, qz = q / C::QQ;
-         double bz[D1D], gz[D1D];
+         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
-         for (int dz = 0; dz < D1D; dz++) { bz[dz] = TB[qz + Q1D*dz]; gz[dz] = TG[qz + Q1D*dz]; }
-         double J[9], dV[9];
-#pragma unroll
-         for (int f = 0; f < 6; f++)
+         for (int dz = 0; dz < D1D; dz++)
          {
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll
-            for (int dz = 0; dz < D1D; dz++)
-            {
-               const int o = col + C::QQ*(dz + D1D*f);
-               g0 += bz[dz]*GB[o]; g1 += bz[dz]*BG[o]; g2 += gz[dz]*BB[o];
-            }
-            if (f < 3) { J[f] = g0; J[f + 3] = g1; J[f + 6] = g2; }
-            else { dV[f - 3] = g0; dV[f] = g1; dV[f + 3] = g2; }
+            const int o = col + C::QQ*(dz + D1D*f);
+            g0 += bz[dz]*GB[o]; g1 += bz[dz]*BG[o]; g2 += gz[dz]*BB[o];
          }
-         const size_t eq = (size_t)e*C::NQ + q;
-         double J0[9], sJ[9];
-         const double *j0 = Jac0inv + eq*9;
-#pragma unroll
-         for (int k = 0; k < 9; k++) { J0[k] = __ldg(j0 + k); }
-         const double dtq = qpoint<3>(J, dV, Eq[q], __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q),
-                                      __ldg(inv_qweights + q), prm, sJ);
-         dt_min = fmin(dt_min, dtq);
-#pragma unroll
-         for (int vd = 0; vd < 3; vd++)
-#pragma unroll
-            for (int gd = 0; gd < 3; gd++) { sJit[eq + NEQ*(gd + vd*3)] = sJ[vd + gd*3]; }
+         if (f < 3) { J[f] = g0; J[f + 3] = g1; J[f + 6] = g2; }
+         else { dV[f - 3] = g0; dV[f] = g1; dV[f + 3] = g2; }
       }
-      __syncthreads();   // A | Bx | Eq are rewritten by the next element
+      const size_t eq = (size_t)e*C::NQ + q;
+      double J0[9], sJ[9];
+      const double *j0 = Jac0inv + eq*9;
+#pragma unroll
+      for (int k = 0; k < 9; k++) { J0[k] = __ldg(j0 + k); }
+      const double dtq = qpoint<3>(J, dV, Eq[q], __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q),
+                                   __ldg(inv_qweights + q), prm, sJ);
+      dt_min = fmin(dt_min, dtq);
+#pragma unroll
+      for (int vd = 0; vd < 3; vd++)
+#pragma unroll
+         for (int gd = 0; gd < 3; gd++) { sJit[eq + NEQ*(gd + vd*3)] = sJ[vd + gd*3]; }
    }
    // block minimum (exact, order independent); NT is a whole number of warps
    for (int o = 16; o > 0; o >>= 1) { dt_min = fmin(dt_min, __shfl_xor_sync(0xffffffffu, dt_min, o)); }

@@ -16,7 +16,7 @@ static int set_smem(K kern, size_t bytes)
 // NTQ and NTF must be multiples of 32 (full-warp shuffles).
 // <D1D, Q1D, NB1, MINB1, NB3, MINB3, NTQ, NBF, NTF>: elements per CTA and minimum resident CTAs
 // for the 1- and 3-component mass apply, threads per element of QUpdate, elements per CTA and
-// threads of Force / Force^T (the L2 mass apply takes 4*NBF elements per 256-thread CTA).
+// threads of Force / Force^T.
 template<int D1D, int Q1D, int NB1, int MINB1, int NB3, int MINB3, int NTQ, int NBF, int NTF>
 struct TunedLaunch3D
 {
@@ -64,16 +64,9 @@ struct TunedLaunch3D
       static_assert(NTQ % 32 == 0 && NTF % 32 == 0, "CTA sizes must be whole warps");
       using Cfg = tuned::QUpd3DCfg<D1D,Q1D>;
       auto kern = tuned::qupdate3d<D1D,Q1D,NTQ,MINB>;
-      static int resident = 0;
-      if (!resident)
-      {
-         int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; }
-         int per_sm = 0, nsm = 0;
-         LAGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTQ, Cfg::SMEM_BYTES));
-         LAGB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device));
-         resident = std::max(1, per_sm)*nsm;   // persistent: one CTA per resident slot
-      }
-      const int grid = std::min(c.NE, resident);
+      static bool attr_set = false;
+      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
+      const int grid = c.NE;
       if (grid > c.part_cap) { set_error("qupdate3d: partial buffer too small"); return LAGB_ERR_STATE; }
       kern<<<grid, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
                                                     c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_part);
@@ -125,7 +118,7 @@ struct TunedLaunch3D
          switch (c.tune[1])
          {
             case 1: return force_launch<2,128>(c, e, v);
-            case 2: return force_launch<1,64>(c, e, v);
+            case 2: return force_launch<4,256>(c, e, v);
             case 3: return force_launch<2,256>(c, e, v);
             case 4: return force_launch<1,128>(c, e, v);
          }
@@ -139,7 +132,7 @@ struct TunedLaunch3D
          switch (c.tune[1])
          {
             case 1: return forcet_launch<2,128>(c, v, e);
-            case 2: return forcet_launch<1,64>(c, v, e);
+            case 2: return forcet_launch<4,256>(c, v, e);
             case 3: return forcet_launch<2,256>(c, v, e);
             case 4: return forcet_launch<1,128>(c, v, e);
          }
@@ -149,7 +142,7 @@ struct TunedLaunch3D
    static int mass_l2(Ctx &c, const double *x, double *y)
    {
       using Cfg = tuned::MassL2Cfg<D1D,Q1D>;
-      constexpr int NB = 4*NBF, NT = 256;
+      constexpr int NB = (Q1D <= 2) ? 64 : (Q1D <= 4) ? 32 : (Q1D <= 6) ? 16 : (Q1D <= 8) ? 8 : 4, NT = 256;
       auto kern = tuned::massl2_3d<D1D,Q1D,NB,NT>;
       constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
       static bool attr_set = false;
@@ -175,7 +168,7 @@ bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D)
       //                          D  Q  NB1 MB1 NB3 MB3 NTQ NBF  NTF
       case 0x22: TunedLaunch3D<2, 2, 64, 1, 32, 1,  32, 16, 128>::install(ks); break;
       case 0x34: TunedLaunch3D<3, 4, 32, 1, 32, 1,  64,  8, 256>::install(ks); break;
-      case 0x46: TunedLaunch3D<4, 6, 32, 2, 16, 3, 224,  4, 256>::install(ks); break;
+      case 0x46: TunedLaunch3D<4, 6, 32, 2, 16, 3, 224,  1,  64>::install(ks); break;
       case 0x58: TunedLaunch3D<5, 8, 16, 1,  8, 1, 256,  2, 256>::install(ks); break;
       case 0x6A: TunedLaunch3D<6, 10, 8, 1,  4, 1, 256,  1, 256>::install(ks); break;
       default: return false;
