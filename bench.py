@@ -183,10 +183,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: laghos_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     lib = load_library()
-    nccl_id = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def fresh_nccl_id():
+        """A new NCCL unique id per run (every lagb_laghos_run creates its own communicator)."""
+        if world == 1:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             import ctypes
@@ -195,12 +199,12 @@ def main():
             idt = torch.tensor(list(buf.raw), dtype=torch.uint8)
         idt = idt.cuda()
         dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
+        return bytes(idt.cpu().tolist())
 
     wl, pg, wl_name = workload(args.gpus, args.rs)
     kw = dict(problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, max_tsteps=args.warmup + args.steps - 1,   # the reference loop runs max_tsteps + 1 steps (laghos.cpp:749-760)
               warmup_steps=args.warmup, kernel_variant=args.variant, device=local, rank=rank, nranks=world,
-              pgrid=pg, nccl_id=nccl_id, **wl)
+              pgrid=pg, **wl)
 
     def barrier():
         if world > 1:
@@ -211,13 +215,13 @@ def main():
     barrier()
     if rank == 0:
         sampler.start()
-    r = run(profile_mass=True, **kw)
+    r = run(profile_mass=True, nccl_id=fresh_nccl_id(), **kw)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e2e = None
     if not args.no_e2e:
         barrier()
-        r2 = run(e2e_host_state=True, **kw)
+        r2 = run(e2e_host_state=True, nccl_id=fresh_nccl_id(), **kw)
         barrier()
         t2 = torch.tensor([r2["device_seconds"]], dtype=torch.float64, device="cuda")
         if world > 1:

@@ -526,8 +526,6 @@ int lagb_qupdate_async(lagb_ctx *h, const double *d_S, double cfl)
    prm.use_viscosity = c.use_visc; prm.use_vorticity = c.use_vort;
    int rc = timer_begin(c, 3); if (rc) { return rc; }
    rc = ks.qupdate(c, d_S, prm); if (rc) { return rc; }
-   pcg::vec_min_reduce<<<1, 256, 0, c.stream>>>(c.dt_nblocks, c.d_part, c.d_dt);
-   LAGB_LAUNCH_CHECK();
    rc = timer_end(c, 3); if (rc) { return rc; }
    c.quad_tstep += c.NE;
    return LAGB_OK;

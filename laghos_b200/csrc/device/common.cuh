@@ -45,6 +45,14 @@ __device__ __forceinline__ void contract(const double *T, const double *in, doub
          }
 }
 
+// running minimum of non-negative doubles (dt estimates): for x, y >= 0 the IEEE bit patterns
+// order like unsigned integers, so one atomicMin per CTA replaces a second reduction pass.
+// min is exact and order independent: deterministic.
+__device__ __forceinline__ void atomic_min_nonneg(double *addr, double v)
+{
+   atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
 struct QPointParams
 {
    double h0, h1order, inv_h1order, cfl, dt_in;

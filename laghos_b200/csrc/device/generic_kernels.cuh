@@ -330,7 +330,7 @@ __global__ void qupdate(const __grid_constant__ DevTables<D1D,Q1D> tab, int NE, 
    {
       double m = smin[0];
       for (int w = 1; w < (blockDim.x + 31)/32; w++) { m = fmin(m, smin[w]); }
-      dt_block_min[blockIdx.x] = m;
+      atomic_min_nonneg(dt_block_min, m);   // dt_block_min: the context's running dt estimate
    }
 }
 

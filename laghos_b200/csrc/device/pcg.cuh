@@ -197,30 +197,60 @@ __global__ void finish_den(State *st, const double *part, int nblocks, int iter)
    }
 }
 
-// x += alpha d ; r -= alpha z ; betanom_part = sum own*r*(dinvm*r)
+// x += alpha d ; r -= alpha z ; betanom_part = sum own*r*(M^-1 r)
+// Branch-free and load-first: a finished component runs with alpha = 0 (x and r are
+// rewritten unchanged), all loads of UNR grid-stride iterations are issued before the first
+// dependent instruction (memory-level parallelism: the kernel is a pure HBM stream).
 template<int NC>
-__global__ void update_xr(int64_t n, int64_t cstride, const State *__restrict__ st,
-                          double *__restrict__ x, double *__restrict__ r, const double *__restrict__ d,
-                          const double *__restrict__ z, const Prec P,
-                          const unsigned char *__restrict__ own, double *__restrict__ part)
+__global__ void __launch_bounds__(RB)
+update_xr(int64_t n, int64_t cstride, const State *__restrict__ st,
+          double *__restrict__ x, double *__restrict__ r, const double *__restrict__ d,
+          const double *__restrict__ z, const Prec P,
+          const unsigned char *__restrict__ own, double *__restrict__ part)
 {
+   constexpr int UNR = 2;
    __shared__ double sh[32];
-   double acc[NC], alpha[NC]; bool skip[NC];
+   double acc[NC], alpha[NC];
 #pragma unroll
-   for (int c = 0; c < NC; c++) { acc[c] = 0.0; alpha[c] = st->alpha[c]; skip[c] = st->done[c] != 0; }
-   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   for (int c = 0; c < NC; c++) { acc[c] = 0.0; alpha[c] = st->done[c] ? 0.0 : st->alpha[c]; }
+   const int64_t stride = (int64_t)gridDim.x*blockDim.x;
+   for (int64_t i0 = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += UNR*stride)
    {
-      const double w = own ? (double)own[i] : 1.0;
+      double xv[UNR][NC], dv[UNR][NC], rv[UNR][NC], zv[UNR][NC], di[UNR], w[UNR];
+      unsigned int em[UNR];
 #pragma unroll
-      for (int c = 0; c < NC; c++)
+      for (int u = 0; u < UNR; u++)
       {
-         if (skip[c]) { continue; }
-         const int64_t k = i + c*cstride;
-         x[k] = x[k] + alpha[c]*d[k];
-         const double rr = r[k] - alpha[c]*z[k];
-         r[k] = rr;
-         const double zz = prec_apply(P, i, c, rr);
-         acc[c] += w*rr*zz;
+         const int64_t i = i0 + u*stride;
+         const bool ok = i < n;
+         di[u] = (ok && P.dinv) ? P.dinv[i] : 1.0;
+         em[u] = (ok && P.ess) ? (unsigned int)P.ess[i] >> P.comp0 : 0u;
+         w[u] = (ok && own) ? (double)own[i] : 1.0;
+#pragma unroll
+         for (int c = 0; c < NC; c++)
+         {
+            const int64_t k = i + c*cstride;
+            xv[u][c] = ok ? x[k] : 0.0; dv[u][c] = ok ? d[k] : 0.0;
+            rv[u][c] = ok ? r[k] : 0.0; zv[u][c] = ok ? z[k] : 0.0;
+         }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+      {
+         const int64_t i = i0 + u*stride;
+         if (i < n)
+         {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+            {
+               const int64_t k = i + c*cstride;
+               x[k] = xv[u][c] + alpha[c]*dv[u][c];
+               const double rr = rv[u][c] - alpha[c]*zv[u][c];
+               r[k] = rr;
+               const double zz = ((em[u] >> c) & 1u) ? 0.0 : di[u]*rr;
+               acc[c] += w[u]*rr*zz;
+            }
+         }
       }
    }
 #pragma unroll
@@ -259,27 +289,51 @@ __global__ void finish_beta(State *st, const double *part, int nblocks, int iter
    st->all_done = all;
 }
 
-// d = dinvm*r + beta d ; z = 0   (skipped for finished components)
+// d = M^-1 r + beta d ; z = 0   (d of a finished component is left as it is)
 template<int NC>
-__global__ void update_d(int64_t n, int64_t cstride, const State *__restrict__ st,
-                         double *__restrict__ d, const double *__restrict__ r,
-                         const Prec P, double *__restrict__ z)
+__global__ void __launch_bounds__(RB)
+update_d(int64_t n, int64_t cstride, const State *__restrict__ st,
+         double *__restrict__ d, const double *__restrict__ r,
+         const Prec P, double *__restrict__ z)
 {
+   constexpr int UNR = 2;
    double beta[NC]; bool skip[NC];
 #pragma unroll
    for (int c = 0; c < NC; c++) { beta[c] = st->beta[c]; skip[c] = st->done[c] != 0; }
-   for (int64_t i = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x*blockDim.x)
+   const int64_t stride = (int64_t)gridDim.x*blockDim.x;
+   for (int64_t i0 = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += UNR*stride)
    {
+      double dv[UNR][NC], rv[UNR][NC], di[UNR];
+      unsigned int em[UNR];
 #pragma unroll
-      for (int c = 0; c < NC; c++)
+      for (int u = 0; u < UNR; u++)
       {
-         const int64_t k = i + c*cstride;
-         if (!skip[c])
+         const int64_t i = i0 + u*stride;
+         const bool ok = i < n;
+         di[u] = (ok && P.dinv) ? P.dinv[i] : 1.0;
+         em[u] = (ok && P.ess) ? (unsigned int)P.ess[i] >> P.comp0 : 0u;
+#pragma unroll
+         for (int c = 0; c < NC; c++)
          {
-            const double zz = prec_apply(P, i, c, r[k]);
-            d[k] = zz + beta[c]*d[k];
+            const int64_t k = i + c*cstride;
+            dv[u][c] = ok ? d[k] : 0.0; rv[u][c] = ok ? r[k] : 0.0;
          }
-         z[k] = 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+      {
+         const int64_t i = i0 + u*stride;
+         if (i < n)
+         {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+            {
+               const int64_t k = i + c*cstride;
+               const double zz = ((em[u] >> c) & 1u) ? 0.0 : di[u]*rv[u][c];
+               d[k] = skip[c] ? dv[u][c] : zz + beta[c]*dv[u][c];
+               z[k] = 0.0;
+            }
+         }
       }
    }
 }

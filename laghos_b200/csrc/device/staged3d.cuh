@@ -270,7 +270,7 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
    {
       double m = red[0];
       for (int w = 1; w < NT/32; w++) { m = fmin(m, red[w]); }
-      dt_block_min[blockIdx.x] = m;
+      atomic_min_nonneg(dt_block_min, m);   // dt_block_min: the context's running dt estimate
    }
 }
 

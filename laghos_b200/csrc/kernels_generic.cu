@@ -51,9 +51,8 @@ struct GenericLaunch
    static int qupdate(Ctx &c, const double *S, const QPointParams &prm)
    {
       const int g = grid(c);
-      if (g > c.part_cap) { set_error("qupdate: partial buffer too small"); return LAGB_ERR_STATE; }
       generic::qupdate<DIM,D1D,Q1D><<<g, BS, 0, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w,
-                                                           c.d_Jac0inv, c.d_gamma, c.d_qweights, prm, c.d_sJit, c.d_part);
+                                                           c.d_Jac0inv, c.d_gamma, c.d_qweights, prm, c.d_sJit, c.d_dt);
       LAGB_LAUNCH_CHECK();
       c.dt_nblocks = g;
       return LAGB_OK;

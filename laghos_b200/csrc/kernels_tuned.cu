@@ -67,9 +67,8 @@ struct TunedLaunch3D
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
       const int grid = c.NE;
-      if (grid > c.part_cap) { set_error("qupdate3d: partial buffer too small"); return LAGB_ERR_STATE; }
       kern<<<grid, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
-                                                    c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_part);
+                                                    c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_dt);
       LAGB_LAUNCH_CHECK();
       c.dt_nblocks = grid;
       return LAGB_OK;
