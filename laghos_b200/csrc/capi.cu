@@ -134,6 +134,47 @@ __global__ void halo_add(int n, int nc, int64_t cstride, const int *__restrict__
    }
 }
 
+// single-phase exchange: pack every (neighbour, shared dof) entry, message layout per
+// neighbour k: [c][j], base offset nc*off[k]
+__global__ void halo_pack_all(int total, int nc, int64_t cstride, const int *__restrict__ idx,
+                              const unsigned char *__restrict__ nbk, const int *__restrict__ off, const int *__restrict__ cnt,
+                              const double *__restrict__ v, double *__restrict__ buf)
+{
+   for (int J = blockIdx.x*blockDim.x + threadIdx.x; J < total; J += gridDim.x*blockDim.x)
+   {
+      const int k = nbk[J], o = off[k], n = cnt[k], j = J - o;
+      const int id = idx[J];
+      for (int c = 0; c < nc; c++) { buf[(size_t)nc*o + (size_t)c*n + j] = v[id + c*cstride]; }
+   }
+}
+// v[dof] = sum over the sharers of dof (own value and received values) in ascending rank order
+__global__ void halo_combine(int nu, int nc, int64_t cstride, const int *__restrict__ u_dof, const int *__restrict__ u_ptr,
+                             const int *__restrict__ u_src, const unsigned char *__restrict__ nbk,
+                             const int *__restrict__ off, const int *__restrict__ cnt,
+                             const double *__restrict__ recv, double *__restrict__ v)
+{
+   for (int u = blockIdx.x*blockDim.x + threadIdx.x; u < nu; u += gridDim.x*blockDim.x)
+   {
+      const int dof = u_dof[u], p0 = u_ptr[u], p1 = u_ptr[u + 1];
+      for (int c = 0; c < nc; c++)
+      {
+         const double own = v[dof + c*cstride];
+         double acc = 0.0;
+         for (int p = p0; p < p1; p++)
+         {
+            const int J = u_src[p];
+            if (J < 0) { acc += own; }
+            else
+            {
+               const int k = nbk[J], o = off[k], n = cnt[k];
+               acc += recv[(size_t)nc*o + (size_t)c*n + (J - o)];
+            }
+         }
+         v[dof + c*cstride] = acc;
+      }
+   }
+}
+
 // Sum the partial values of shared dofs over the ranks that share them
 // (P^t then P in the reference's RAP operator, laghos_assembly.cpp:95 / SURVEY 8e):
 // per phase, pack -> grouped ncclSend/ncclRecv -> add.  After all phases every
@@ -141,6 +182,24 @@ __global__ void halo_add(int n, int nc, int64_t cstride, const int *__restrict__
 int halo_sum(Ctx &c, double *v, int nc)
 {
    if (c.nranks <= 1 || c.nbrs.empty()) { return LAGB_OK; }
+   if (c.halo_single)
+   {
+      const int g = std::max(1, std::min(1024, (c.halo_total + 255)/256));
+      halo_pack_all<<<g, 256, 0, c.stream>>>(c.halo_total, nc, c.ndofs, c.d_pack_idx, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, v, c.d_send_all);
+      LAGB_LAUNCH_CHECK();
+      LAGB_NCCL(g_nccl.GroupStart());
+      for (size_t k = 0; k < c.nbrs.size(); k++)
+      {
+         const size_t o = (size_t)nc*c.h_nbr_off[k], n = (size_t)nc*c.h_nbr_n[k];
+         LAGB_NCCL(g_nccl.Send(c.d_send_all + o, n, NCCL_F64, c.nbrs[k].rank, c.nccl_comm, c.stream));
+         LAGB_NCCL(g_nccl.Recv(c.d_recv_all + o, n, NCCL_F64, c.nbrs[k].rank, c.nccl_comm, c.stream));
+      }
+      LAGB_NCCL(g_nccl.GroupEnd());
+      halo_combine<<<std::max(1, std::min(1024, (c.halo_nu + 255)/256)), 256, 0, c.stream>>>(
+         c.halo_nu, nc, c.ndofs, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, c.d_recv_all, v);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
    for (int ph = 0; ph < c.nphases; ph++)
    {
       bool any = false;
@@ -231,7 +290,7 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    auto reduced = [&](int nblocks, double *tmp, const double *&src, int &nsrc) -> int
    {
       if (c.nranks <= 1) { src = c.d_part; nsrc = nblocks; return LAGB_OK; }
-      pcg::reduce_partials<NC><<<1, pcg::RB, 0, c.stream>>>(nblocks, c.d_part, tmp);
+      pcg::reduce_final<NC><<<1, pcg::FB, 0, c.stream>>>(nblocks, c.d_part, tmp);
       LAGB_LAUNCH_CHECK();
       int rc = allreduce_sum(c, tmp, NC); if (rc) { return rc; }
       src = tmp; nsrc = 1;
@@ -393,6 +452,8 @@ void lagb_ctx_destroy(lagb_ctx *h)
                    c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
+   void *hp[] = {c.d_pack_idx, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_send_all, c.d_recv_all};
+   for (void *p : hp) { if (p) { cudaFree(p); } }
    if (c.h_state) { cudaFreeHost(c.h_state); }
    if (c.h_scal) { cudaFreeHost(c.h_scal); }
    for (int w = 0; w < Timer::NT; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
@@ -705,6 +766,43 @@ int lagb_ctx_comm_init(lagb_ctx *h, const uint8_t id[128], int rank, int nranks,
       c.nphases = std::max(c.nphases, nb.phase + 1);
    }
    if (h_owner_mask) { rc = dev_upload(&c.d_own, (const unsigned char*)h_owner_mask, (size_t)c.ndofs); if (rc) { return rc; } }
+   // all neighbours in phase 0: single-phase exchange with rank-ordered summation
+   c.halo_single = (nnbr > 0 && c.nphases == 1 && nnbr < 255);
+   if (c.halo_single)
+   {
+      std::vector<int> pack_idx, off(nnbr), cnt(nnbr);
+      std::vector<unsigned char> nbk;
+      int total = 0;
+      for (int k = 0; k < nnbr; k++)
+      {
+         off[k] = total; cnt[k] = nshared[k];
+         for (int j = 0; j < nshared[k]; j++) { pack_idx.push_back(h_shared_dofs[k][j]); nbk.push_back((unsigned char)k); }
+         total += nshared[k];
+      }
+      // per shared dof: (rank, source) pairs, self = -1, sorted by rank
+      std::vector<std::vector<std::pair<int,int>>> per((size_t)c.ndofs);
+      for (int J = 0; J < total; J++) { per[pack_idx[J]].push_back({nbr_rank[nbk[J]], J}); }
+      std::vector<int> u_dof, u_ptr(1, 0), u_src;
+      for (int64_t i = 0; i < c.ndofs; i++)
+      {
+         if (per[i].empty()) { continue; }
+         per[i].push_back({rank, -1});
+         std::sort(per[i].begin(), per[i].end());
+         u_dof.push_back((int)i);
+         for (auto &pr : per[i]) { u_src.push_back(pr.second); }
+         u_ptr.push_back((int)u_src.size());
+      }
+      c.halo_total = total; c.halo_nu = (int)u_dof.size(); c.h_nbr_off = off; c.h_nbr_n = cnt;
+      rc = dev_upload(&c.d_pack_idx, pack_idx.data(), pack_idx.size()); if (rc) { return rc; }
+      rc = dev_upload(&c.d_pack_nb, nbk.data(), nbk.size()); if (rc) { return rc; }
+      rc = dev_upload(&c.d_nbr_off, off.data(), off.size()); if (rc) { return rc; }
+      rc = dev_upload(&c.d_nbr_n, cnt.data(), cnt.size()); if (rc) { return rc; }
+      rc = dev_upload(&c.d_u_dof, u_dof.data(), u_dof.size()); if (rc) { return rc; }
+      rc = dev_upload(&c.d_u_ptr, u_ptr.data(), u_ptr.size()); if (rc) { return rc; }
+      rc = dev_upload(&c.d_u_src, u_src.data(), u_src.size()); if (rc) { return rc; }
+      rc = dev_alloc(&c.d_send_all, (size_t)total*3); if (rc) { return rc; }
+      rc = dev_alloc(&c.d_recv_all, (size_t)total*3); if (rc) { return rc; }
+   }
    return LAGB_OK;
 }
 

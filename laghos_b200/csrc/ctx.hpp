@@ -80,6 +80,13 @@ struct Ctx
    int rank = 0, nranks = 1; void *nccl_comm = nullptr;
    struct Nbr { int rank, phase, n; int *d_idx; double *d_send, *d_recv; };
    std::vector<Nbr> nbrs; int nphases = 0;
+   // single-phase exchange (all sharers at once, contributions summed in ascending rank order)
+   bool halo_single = false;
+   int halo_total = 0, halo_nu = 0;                 // concatenated shared entries, distinct shared dofs
+   std::vector<int> h_nbr_off, h_nbr_n;             // per neighbour: offset / count in the concatenation
+   int *d_pack_idx = nullptr, *d_nbr_off = nullptr, *d_nbr_n = nullptr, *d_u_dof = nullptr, *d_u_ptr = nullptr, *d_u_src = nullptr;
+   unsigned char *d_pack_nb = nullptr;
+   double *d_send_all = nullptr, *d_recv_all = nullptr;
    int64_t ne_global = 0;
 };
 

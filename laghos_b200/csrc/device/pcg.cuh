@@ -149,6 +149,16 @@ __device__ __forceinline__ void reduce_to_thread0(const double *__restrict__ par
    }
 }
 
+// multi-rank path: partials -> NC sums (input of the NCCL all-reduce)
+template<int NC>
+__global__ void reduce_final(int nblocks, const double *__restrict__ part, double *__restrict__ out)
+{
+   __shared__ double sh[32];
+   double tmp[NC];
+   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (threadIdx.x == 0) { for (int c = 0; c < NC; c++) { out[c] = tmp[c]; } }
+}
+
 // The finish kernels take the per-block partials straight from the producing kernel
 // (nblocks > 1, single rank) or the already reduced and all-reduced sums (nblocks == 1).
 template<int NC>

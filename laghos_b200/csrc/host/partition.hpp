@@ -4,9 +4,9 @@
 // NVSwitch box.  Each rank owns a box of elements; H1 dofs on box faces are
 // duplicated on the sharing ranks.  This header computes, for one rank,
 //   * its element box,
-//   * the neighbour list with the shared scalar-dof indices in matching order and an
-//     exchange phase per neighbour (phase = axis: three successive face exchanges sum
-//     edge and corner dofs over all sharers, like P^t followed by P),
+//   * the list of all ranks sharing dofs with it (face, edge and corner neighbours) with the
+//     shared scalar-dof indices in matching (lexicographic lattice) order; one exchange phase,
+//     contributions summed in ascending rank order (P^t followed by P in the reference),
 //   * the owner mask used in inner products (each shared dof counted once).
 #pragma once
 #include <vector>
@@ -51,28 +51,44 @@ struct Partition
       const int64_t nd = (int64_t)N1[0]*N1[1]*N1[2];
       owner.assign((size_t)nd, 1);
       nbrs.clear();
-      for (int d = 0; d < dim; d++)
-      {
-         for (int side = 0; side < 2; side++)
-         {
-            const int nc = pc[d] + (side ? 1 : -1);
-            if (nc < 0 || nc >= pgrid[d]) { continue; }
-            int q[3] = {pc[0], pc[1], pc[2]}; q[d] = nc;
-            Nbr nb; nb.rank = q[0] + pgrid[0]*(q[1] + pgrid[1]*q[2]); nb.phase = d;
-            const int plane = side ? N1[d] - 1 : 0;
-            for (int gz = 0; gz < N1[2]; gz++)
-               for (int gy = 0; gy < N1[1]; gy++)
-                  for (int gx = 0; gx < N1[0]; gx++)
-                  {
-                     const int g[3] = {gx, gy, gz};
-                     if (g[d] != plane) { continue; }
-                     const int id = gx + N1[0]*(gy + N1[1]*gz);
-                     nb.dofs.push_back(id);
-                     if (side == 0) { owner[id] = 0; }   // the lower neighbour owns the interface
-                  }
-            nbrs.push_back(std::move(nb));
-         }
-      }
+      // All ranks that share at least one dof (faces, edges and corners: up to 26), one
+      // exchange phase: every sharer sends its partial value to every other sharer and the
+      // receiver sums the contributions in ascending rank order (the same order on every
+      // sharer, so the copies of a shared dof stay bit-identical across ranks).
+      for (int oz = -1; oz <= 1; oz++)
+         for (int oy = -1; oy <= 1; oy++)
+            for (int ox = -1; ox <= 1; ox++)
+            {
+               const int off[3] = {ox, oy, oz};
+               if (ox == 0 && oy == 0 && oz == 0) { continue; }
+               int q[3]; bool ok_n = true;
+               for (int d = 0; d < 3; d++)
+               {
+                  q[d] = pc[d] + off[d];
+                  if (d >= dim && off[d] != 0) { ok_n = false; }
+                  if (q[d] < 0 || q[d] >= pgrid[d]) { ok_n = false; }
+               }
+               if (!ok_n) { continue; }
+               Nbr nb; nb.rank = q[0] + pgrid[0]*(q[1] + pgrid[1]*q[2]); nb.phase = 0;
+               int lo_i[3], hi_i[3];
+               for (int d = 0; d < 3; d++)
+               {
+                  lo_i[d] = (off[d] == 1) ? N1[d] - 1 : 0;
+                  hi_i[d] = (off[d] == -1) ? 0 : N1[d] - 1;
+               }
+               for (int gz = lo_i[2]; gz <= hi_i[2]; gz++)
+                  for (int gy = lo_i[1]; gy <= hi_i[1]; gy++)
+                     for (int gx = lo_i[0]; gx <= hi_i[0]; gx++) { nb.dofs.push_back(gx + N1[0]*(gy + N1[1]*gz)); }
+               nbrs.push_back(std::move(nb));
+            }
+      // a dof on a lower face of the box belongs to a lower rank
+      for (int gz = 0; gz < N1[2]; gz++)
+         for (int gy = 0; gy < N1[1]; gy++)
+            for (int gx = 0; gx < N1[0]; gx++)
+            {
+               const int g[3] = {gx, gy, gz};
+               for (int d = 0; d < dim; d++) { if (g[d] == 0 && pc[d] > 0) { owner[gx + N1[0]*(gy + N1[1]*gz)] = 0; } }
+            }
    }
 };
 
