@@ -41,7 +41,7 @@ struct Mass3DCfg
    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*ND*sizeof(int);
 };
 
-template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB>
+template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_SCATTER>
 __global__ void __launch_bounds__(((NC*NB*D1D + 31)/32)*32, MINB)
 mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t cstride,
        const int *__restrict__ map, const double *__restrict__ Dq,
@@ -208,29 +208,51 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
             Z[qx][dy] = z;
          }
       }
-      // all plane reads of this thread are complete (Z holds them): safe to overwrite
-#pragma unroll
-      for (int dy = 0; dy < D1D; dy++)
-#pragma unroll
-         for (int dx = 0; dx < D1D; dx++)
-         {
-            double o = 0.0;
-#pragma unroll
-            for (int qx = 0; qx < Q1D; qx++) { o += tab.B[qx + Q1D*dx]*Z[qx][dy]; }
-            pl[dx + D1D*dy] = o;
-         }
-   }
-   __syncthreads();
-   // ---- phase D: cooperative scatter-add (red.global.add.f64), lanes along the dof index ----
-   for (int it = t; it < nel*C::ND; it += C::T)
-   {
-      const int e2 = it / C::ND, i = it - e2*C::ND;
-      const int id = sIdx[it];
-      const int z = i / C::DD, ixy = i - z*C::DD;
-#pragma unroll
-      for (int cc = 0; cc < NC; cc++)
+      if (DIRECT_SCATTER)
       {
-         atomicAdd(y + (size_t)cc*cstride + id, sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy]);
+         // scatter-add straight from registers (restriction indices of the slice from smem)
+         const int *ids = sIdx + e_loc*C::ND + dz*C::DD;
+         double *yc = y + (size_t)c*cstride;
+#pragma unroll
+         for (int dy = 0; dy < D1D; dy++)
+#pragma unroll
+            for (int dx = 0; dx < D1D; dx++)
+            {
+               double o = 0.0;
+#pragma unroll
+               for (int qx = 0; qx < Q1D; qx++) { o += tab.B[qx + Q1D*dx]*Z[qx][dy]; }
+               atomicAdd(yc + ids[dx + D1D*dy], o);
+            }
+      }
+      else
+      {
+         // all plane reads of this thread are complete (Z holds them): safe to overwrite
+#pragma unroll
+         for (int dy = 0; dy < D1D; dy++)
+#pragma unroll
+            for (int dx = 0; dx < D1D; dx++)
+            {
+               double o = 0.0;
+#pragma unroll
+               for (int qx = 0; qx < Q1D; qx++) { o += tab.B[qx + Q1D*dx]*Z[qx][dy]; }
+               pl[dx + D1D*dy] = o;
+            }
+      }
+   }
+   if (!DIRECT_SCATTER)
+   {
+      __syncthreads();
+      // ---- phase D: cooperative scatter-add (red.global.add.f64), lanes along the dof index ----
+      for (int it = t; it < nel*C::ND; it += C::T)
+      {
+         const int e2 = it / C::ND, i = it - e2*C::ND;
+         const int id = sIdx[it];
+         const int z = i / C::DD, ixy = i - z*C::DD;
+#pragma unroll
+         for (int cc = 0; cc < NC; cc++)
+         {
+            atomicAdd(y + (size_t)cc*cstride + id, sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy]);
+         }
       }
    }
    if (WITH_DEN)

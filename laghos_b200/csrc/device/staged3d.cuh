@@ -396,9 +396,23 @@ struct ForceT3DCfg
    static constexpr int S_A = (3*S_ST2 > NF*ND) ? 3*S_ST2 : NF*ND;
    static constexpr int S_B = (2*S_ST1 > S_E2) ? 2*S_ST1 : S_E2;
    static constexpr int PER_ELEM = S_A + S_B;
+   static constexpr int S_PF = 9*NQ;             // stressJinvT slab of one element (prefetch variant)
 };
 
-template<int D1D, int Q1D, int NB, int NT>
+// 16-byte asynchronous global->shared copy (LDGSTS): no register staging, completes in the
+// background while the gather and the x/y pencils run
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+   asm volatile("cp.async.commit_group;" ::: "memory");
+   asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template<int D1D, int Q1D, int NB, int NT, bool PREFETCH>
 __global__ void __launch_bounds__(NT)
 forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t ndofs,
          const int *__restrict__ map, const double *__restrict__ sJit,
@@ -414,6 +428,21 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
    const int eb = blockIdx.x*NB;
    const int nel = min(NB, NE - eb);
    const size_t NEQ = (size_t)NE*C::NQ;
+   double *Ss = smem + NB*PE;                    // [e][cg][q], PREFETCH only
+   if (PREFETCH)
+   {
+      // the element's 9 stressJinvT planes stream into shared memory while the gather and
+      // the x/y pencils run (NQ is even and the planes are 16-byte aligned)
+      static_assert(C::NQ % 2 == 0, "16-byte chunks");
+      constexpr int NCH = 9*C::NQ/2;
+      for (int it = tid; it < nel*NCH; it += NT)
+      {
+         const int e = it / NCH, r = it - e*NCH;
+         const int cg = r / (C::NQ/2), h = r - cg*(C::NQ/2);
+         cp_async16(Ss + (size_t)e*C::S_PF + cg*C::NQ + 2*h, sJit + (size_t)(eb + e)*C::NQ + NEQ*cg + 2*h);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+   }
    for (int it = tid; it < nel*C::NF*C::ND; it += NT)
    {
       const int e = it / (C::NF*C::ND), r = it - e*(C::NF*C::ND);
@@ -422,6 +451,11 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
    }
    __syncthreads();
    grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, nel, Vs, PE, Bx, Gx, PE, BB, GB, BG, PE, tid, NT);
+   if (PREFETCH)
+   {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+   }
    // z pencils (e, column): gradients at the Q1D points of the column, contraction with
    // stressJinvT, then the z pencil of the transposed L2 interpolation in registers
    for (int it = tid; it < nel*QQ; it += NT)
@@ -448,8 +482,16 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
          for (int qz = 0; qz < Q1D; qz++)
          {
             // same association as the reference (:889-899): per component, sum over g, then add
-            const double *sq = s + QQ*qz;
-            acc[qz] += g0[qz]*__ldg(sq + NEQ*(0 + 3*c)) + g1[qz]*__ldg(sq + NEQ*(1 + 3*c)) + g2[qz]*__ldg(sq + NEQ*(2 + 3*c));
+            if (PREFETCH)
+            {
+               const double *sq = Ss + (size_t)e*C::S_PF + col + QQ*qz;
+               acc[qz] += g0[qz]*sq[C::NQ*(0 + 3*c)] + g1[qz]*sq[C::NQ*(1 + 3*c)] + g2[qz]*sq[C::NQ*(2 + 3*c)];
+            }
+            else
+            {
+               const double *sq = s + QQ*qz;
+               acc[qz] += g0[qz]*__ldg(sq + NEQ*(0 + 3*c)) + g1[qz]*__ldg(sq + NEQ*(1 + 3*c)) + g2[qz]*__ldg(sq + NEQ*(2 + 3*c));
+            }
          }
       }
       double o[C::L1D];

@@ -23,11 +23,11 @@ struct TunedLaunch3D
    using Tab = DevTables<D1D,Q1D>;
    static const Tab &tab(Ctx &c) { return *reinterpret_cast<const Tab*>(c.tab_blob.data()); }
 
-   template<int NC, bool WITH_DEN, int NB, int MINB>
+   template<int NC, bool WITH_DEN, int NB, int MINB, bool DS = false>
    static int mass_launch_v(Ctx &c, const double *x, double *y)
    {
       using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
-      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB>;
+      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB,DS>;
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
       const int grid = (c.NE + NB - 1)/NB;
@@ -44,9 +44,9 @@ struct TunedLaunch3D
       {
          switch (c.tune[0])
          {
-            case 1: return mass_launch_v<NC,WITH_DEN,16,2>(c, x, y);
+            case 1: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
             case 2: return mass_launch_v<NC,WITH_DEN,8,7>(c, x, y);
-            case 3: return mass_launch_v<NC,WITH_DEN,32,1>(c, x, y);
+            case 3: return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,8,6>(c, x, y);
          }
       }
@@ -98,12 +98,12 @@ struct TunedLaunch3D
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
-   template<int NB, int NT>
+   template<int NB, int NT, bool PF = false>
    static int forcet_launch(Ctx &c, const double *v, double *e)
    {
       using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
-      auto kern = tuned::forcet3d<D1D,Q1D,NB,NT>;
-      constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
+      auto kern = tuned::forcet3d<D1D,Q1D,NB,NT,PF>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + (PF ? Cfg::S_PF : 0));
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
@@ -130,10 +130,10 @@ struct TunedLaunch3D
       {
          switch (c.tune[1])
          {
-            case 1: return forcet_launch<2,128>(c, v, e);
+            case 1: return forcet_launch<1,64,true>(c, v, e);
             case 2: return forcet_launch<4,256>(c, v, e);
-            case 3: return forcet_launch<2,256>(c, v, e);
-            case 4: return forcet_launch<1,128>(c, v, e);
+            case 3: return forcet_launch<2,128,true>(c, v, e);
+            case 4: return forcet_launch<1,96,true>(c, v, e);
          }
       }
       return forcet_launch<NBF,NTF>(c, v, e);

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--mesh", default="cube01_hex")
     ap.add_argument("--problem", type=int, default=1)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--no-pcg", action="store_true")
     ap.add_argument("--mass-variants", default="0,1,2,3,4")
     ap.add_argument("--force-variants", default="0,1,2,3,4")
     ap.add_argument("--q-variants", default="0,1,2")
@@ -63,24 +64,25 @@ def main():
 
     rows = []
 
-    def report(name, us, gbytes):
+    def report(name, us, gbytes, out=None):
         bw = gbytes / (us * 1e-6)
         rows.append((name, us, gbytes, bw, bw / peak))
-        print(f"{name:34s} {us:10.1f} us  {gbytes:7.3f} GB  {bw:8.1f} GB/s  {100 * bw / peak:5.1f}% of {peak:.0f}", flush=True)
+        chk = "" if out is None else f"  checksum {float(out.double().abs().sum()):.15e}"
+        print(f"{name:38s} {us:10.1f} us  {gbytes:7.3f} GB  {bw:8.1f} GB/s  {100 * bw / peak:5.1f}% of {peak:.0f}{chk}", flush=True)
 
     dim = P.dim
     for var in [int(s) for s in args.q_variants.split(",")]:
         c.tune(2, var)
         report(f"qupdate (fused) variant {var}", timeit(lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
-               8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)))
+               8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)), c.qdata(0))
     c.tune(2, 0)
     ye = c.empty(nl)
     for var in [int(s) for s in args.force_variants.split(",")]:
         c.tune(1, var)
         report(f"force_mult variant {var}", timeit(lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
-               8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+               8e-9 * (dim * dim * NE * NQ + nl + dim * nd), yv)
         report(f"force_mult_transpose variant {var}", timeit(lambda: c.lib.lagb_force_mult_transpose(c.h, c._p(v), c._p(ye))),
-               8e-9 * (dim * dim * NE * NQ + nl + dim * nd))
+               8e-9 * (dim * dim * NE * NQ + nl + dim * nd), ye)
     c.tune(1, 0)
     y1 = c.empty(nd)
     report("vmass_mult (1 comp)", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
@@ -88,9 +90,12 @@ def main():
     for var in [int(s) for s in args.mass_variants.split(",")]:
         c.tune(0, var)
         report(f"vmass_mult_all (3 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
-               8e-9 * (NE * NQ + 2 * dim * nd))
+               8e-9 * (NE * NQ + 2 * dim * nd), yv)
     c.tune(0, 0)
     report("emass_mult (L2)", timeit(lambda: c.lib.lagb_emass_mult(c.h, c._p(e), c._p(ye))), 8e-9 * (NE * NQ + 2 * nl))
+    if args.no_pcg:
+        c.close()
+        return
     b = c.dev(rng.uniform(-1, 1, nv))
     xs = c.zeros(nv)
 
