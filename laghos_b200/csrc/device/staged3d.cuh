@@ -51,6 +51,19 @@ __device__ __forceinline__ void pencil_bwd(const double *T, const double (&in)[Q
    }
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS): no register staging, completes in the
+// background while the gather and the x/y pencils run
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+   asm volatile("cp.async.commit_group;" ::: "memory");
+   asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------
 // L2 (Bernstein) dofs -> values at quadrature points for NB elements.
 // Es[e][NL] -> Eq[e][NQ]; scratch t1[e][L*L*Q], t2[e][L*Q*Q].  Ends with a barrier.
@@ -290,7 +303,7 @@ struct Force3DCfg
    static constexpr int PER_ELEM = S_W + S_R2;
 };
 
-template<int D1D, int Q1D, int NB, int NT>
+template<int D1D, int Q1D, int NB, int NT, bool PREFETCH>
 __global__ void __launch_bounds__(NT)
 force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t ndofs,
         const int *__restrict__ map, const double *__restrict__ sJit,
@@ -307,6 +320,19 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    const int eb = blockIdx.x*NB;
    const int nel = min(NB, NE - eb);
    const size_t NEQ = (size_t)NE*C::NQ;
+   double *Ss = smem + NB*PE;                    // [e][cg][q], PREFETCH only
+   if (PREFETCH)
+   {
+      static_assert(C::NQ % 2 == 0, "16-byte chunks");
+      constexpr int NCH = 9*C::NQ/2;
+      for (int it = tid; it < nel*NCH; it += NT)
+      {
+         const int e = it / NCH, r = it - e*NCH;
+         const int cg = r / (C::NQ/2), h = r - cg*(C::NQ/2);
+         cp_async16(Ss + (size_t)e*9*C::NQ + cg*C::NQ + 2*h, sJit + (size_t)(eb + e)*C::NQ + NEQ*cg + 2*h);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+   }
    for (int it = tid; it < nel*C::NL; it += NT)
    {
       const int e = it / C::NL, i = it - e*C::NL;
@@ -314,15 +340,21 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    }
    __syncthreads();
    l2_values<C::L1D,Q1D>(tab.BL, nel, Es, PE, E1, PE, E2, PE, Eq, PE, tid, NT);
+   if (PREFETCH)
+   {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+   }
    // z pencils (e, c, g, column): W[c][g][dz][col] = sum_qz Tz(qz,dz) sJit(q,g,c) Eq(q), Tz = G for g == 2
    for (int it = tid; it < nel*9*QQ; it += NT)
    {
       const int e = it / (9*QQ), r = it - e*(9*QQ);
       const int col = r % QQ, cg = r / QQ;      // cg = g + 3*c
       const double *s = sJit + (size_t)(eb + e)*C::NQ + NEQ*cg + col;
+      const double *ss = Ss + (size_t)e*9*C::NQ + cg*C::NQ + col;
       double sv[Q1D], w[D1D];
 #pragma unroll
-      for (int qz = 0; qz < Q1D; qz++) { sv[qz] = __ldg(s + QQ*qz); }
+      for (int qz = 0; qz < Q1D; qz++) { sv[qz] = PREFETCH ? ss[QQ*qz] : __ldg(s + QQ*qz); }
 #pragma unroll
       for (int qz = 0; qz < Q1D; qz++) { sv[qz] *= Eq[e*PE + col + QQ*qz]; }
       if (cg % 3 == 2) { pencil_bwd<D1D,Q1D>(tab.G, sv, w); }
@@ -398,19 +430,6 @@ struct ForceT3DCfg
    static constexpr int PER_ELEM = S_A + S_B;
    static constexpr int S_PF = 9*NQ;             // stressJinvT slab of one element (prefetch variant)
 };
-
-// 16-byte asynchronous global->shared copy (LDGSTS): no register staging, completes in the
-// background while the gather and the x/y pencils run
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all()
-{
-   asm volatile("cp.async.commit_group;" ::: "memory");
-   asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
 
 template<int D1D, int Q1D, int NB, int NT, bool PREFETCH>
 __global__ void __launch_bounds__(NT)

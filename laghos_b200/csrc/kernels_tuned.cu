@@ -46,9 +46,10 @@ struct TunedLaunch3D
          {
             case 1: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
             case 2: return mass_launch_v<NC,WITH_DEN,8,7>(c, x, y);
-            case 3: return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);
+            case 3: return mass_launch_v<NC,WITH_DEN,16,3>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,8,6>(c, x, y);
          }
+         return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1.txt)
       }
       return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3>(c, x, y);
    }
@@ -79,19 +80,20 @@ struct TunedLaunch3D
       {
          switch (c.tune[2])
          {
-            case 1: return qupdate_launch<3>(c, S, prm);
+            case 1: return qupdate_launch<2>(c, S, prm);
             case 2: return qupdate_launch<1>(c, S, prm);
          }
-         return qupdate_launch<2>(c, S, prm);
+         return qupdate_launch<3>(c, S, prm);   // 3 CTAs/SM (80 registers, small L1-resident spill) beats 2 CTAs at 128
       }
-      return qupdate_launch<1>(c, S, prm);
+      if (Q1D >= 10 || c.tune[2] == 1) { return qupdate_launch<1>(c, S, prm); }   // Q1D = 10: one CTA per SM by shared memory
+      return qupdate_launch<2>(c, S, prm);
    }
-   template<int NB, int NT>
+   template<int NB, int NT, bool PF = false>
    static int force_launch(Ctx &c, const double *e, double *v)
    {
       using Cfg = tuned::Force3DCfg<D1D,Q1D>;
-      auto kern = tuned::force3d<D1D,Q1D,NB,NT>;
-      constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
+      auto kern = tuned::force3d<D1D,Q1D,NB,NT,PF>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + (PF ? 9*Cfg::NQ : 0));
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
@@ -116,10 +118,10 @@ struct TunedLaunch3D
       {
          switch (c.tune[1])
          {
-            case 1: return force_launch<2,128>(c, e, v);
+            case 1: return force_launch<1,64,true>(c, e, v);
             case 2: return force_launch<4,256>(c, e, v);
-            case 3: return force_launch<2,256>(c, e, v);
-            case 4: return force_launch<1,128>(c, e, v);
+            case 3: return force_launch<1,96,true>(c, e, v);
+            case 4: return force_launch<2,128,true>(c, e, v);
          }
       }
       return force_launch<NBF,NTF>(c, e, v);
@@ -132,9 +134,10 @@ struct TunedLaunch3D
          {
             case 1: return forcet_launch<1,64,true>(c, v, e);
             case 2: return forcet_launch<4,256>(c, v, e);
-            case 3: return forcet_launch<2,128,true>(c, v, e);
-            case 4: return forcet_launch<1,96,true>(c, v, e);
+            case 3: return forcet_launch<1,128,true>(c, v, e);
+            case 4: return forcet_launch<1,64>(c, v, e);
          }
+         return forcet_launch<1,96,true>(c, v, e);   // cp.async prefetch of the stressJinvT slab
       }
       return forcet_launch<NBF,NTF>(c, v, e);
    }

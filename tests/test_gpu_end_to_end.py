@@ -42,7 +42,10 @@ def test_checks_table_gpu(built, dim, problem, variant):
     dict(mesh="cube01_hex", rs=2, problem=0, ok=3, ot=2, max_tsteps=12),   # BASELINE config 3 at rs 2
     dict(mesh="box01_hex", rs=1, problem=3, ok=2, ot=1, max_tsteps=12),    # BASELINE config 5, ok 2
     dict(mesh="square01_quad", rs=3, problem=0, ok=2, ot=1, max_tsteps=20),  # BASELINE config 1
-], ids=["sedov-q3q2", "tg-q3q2", "triple-q2q1", "tg2d-q2q1"])
+    dict(mesh="box01_hex", rs=1, problem=3, ok=3, ot=2, max_tsteps=6),     # BASELINE config 5, ok 3
+    dict(mesh="box01_hex", rs=0, problem=3, ok=4, ot=3, max_tsteps=6),     # BASELINE config 5, ok 4
+    dict(mesh="box01_hex", rs=0, problem=3, ok=5, ot=4, max_tsteps=4),     # BASELINE config 5, ok 5 (no reference kernel)
+], ids=["sedov-q3q2", "tg-q3q2", "triple-q2q1", "tg2d-q2q1", "triple-q3q2", "triple-q4q3", "triple-q5q4"])
 def test_vs_oracle_e_norm(built, cfg, batched):
     from laghos_b200.api import run
     kw = dict(cfg, t_final=10.0, cg_tol=1e-12)
@@ -60,6 +63,17 @@ def test_readme_run2_gpu(built):
     """README.md:216,228: -p 0 -m cube01_hex -rs 1 -tf 0.75 -pa -> 1041 steps, dt 0.000121, |e| 3.3909635545e+03."""
     from laghos_b200.api import run
     g = TABLE["readme"]["run2"]
+    r = run(**g["args"])
+    assert r["ti_last"] == g["step"]
+    assert f"{r['dt']:.6f}" == g["dt"]
+    assert f"{r['e_norm']:.10e}" == g["e_norm"]
+
+
+def test_readme_run8_rk2avg_gpu(built):
+    """README.md:222,234: -p 4 -m square_gresho -rs 3 -ok 3 -ot 2 -tf 0.62831853 -s 7 -pa (RK2Avg, Q3Q2 2D):
+    776 steps, dt 0.000045, |e| 4.0982431726e+02."""
+    from laghos_b200.api import run
+    g = TABLE["readme"]["run8"]
     r = run(**g["args"])
     assert r["ti_last"] == g["step"]
     assert f"{r['dt']:.6f}" == g["dt"]
