@@ -44,12 +44,22 @@ struct TunedLaunch3D
       {
          switch (c.tune[0])
          {
-            case 1: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
-            case 2: return mass_launch_v<NC,WITH_DEN,8,7>(c, x, y);
-            case 3: return mass_launch_v<NC,WITH_DEN,16,3>(c, x, y);
-            case 4: return mass_launch_v<NC,WITH_DEN,8,6>(c, x, y);
+            case 1: return mass_launch_v<NC,WITH_DEN,8,7,true>(c, x, y);
+            case 2: return mass_launch_v<NC,WITH_DEN,4,12,true>(c, x, y);
+            case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
+            case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
          }
-         return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1.txt)
+         return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants.txt)
+      }
+      if constexpr (NC == 1 && D1D == 4)   // single-component apply (lagb_tune_set key 3)
+      {
+         switch (c.tune[3])
+         {
+            case 1: return mass_launch_v<NC,WITH_DEN,32,2,true>(c, x, y);
+            case 2: return mass_launch_v<NC,WITH_DEN,16,4,true>(c, x, y);
+            case 3: return mass_launch_v<NC,WITH_DEN,16,8,true>(c, x, y);
+            case 4: return mass_launch_v<NC,WITH_DEN,8,8,true>(c, x, y);
+         }
       }
       return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3>(c, x, y);
    }
@@ -82,6 +92,7 @@ struct TunedLaunch3D
          {
             case 1: return qupdate_launch<2>(c, S, prm);
             case 2: return qupdate_launch<1>(c, S, prm);
+            case 3: return qupdate_launch<4>(c, S, prm);
          }
          return qupdate_launch<3>(c, S, prm);   // 3 CTAs/SM (80 registers, small L1-resident spill) beats 2 CTAs at 128
       }

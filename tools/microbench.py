@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--mass-variants", default="0,1,2,3,4")
     ap.add_argument("--force-variants", default="0,1,2,3,4")
     ap.add_argument("--q-variants", default="0,1,2")
+    ap.add_argument("--mass1-variants", default="0")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -85,8 +86,11 @@ def main():
                8e-9 * (dim * dim * NE * NQ + nl + dim * nd), ye)
     c.tune(1, 0)
     y1 = c.empty(nd)
-    report("vmass_mult (1 comp)", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
-           8e-9 * (NE * NQ + 2 * nd))
+    for var in [int(s) for s in args.mass1_variants.split(",")]:
+        c.tune(3, var)
+        report(f"vmass_mult (1 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
+               8e-9 * (NE * NQ + 2 * nd), y1)
+    c.tune(3, 0)
     for var in [int(s) for s in args.mass_variants.split(",")]:
         c.tune(0, var)
         report(f"vmass_mult_all (3 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
