@@ -58,8 +58,9 @@ struct TunedLaunch3D
             case 1: return mass_launch_v<NC,WITH_DEN,32,2,true>(c, x, y);
             case 2: return mass_launch_v<NC,WITH_DEN,16,4,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,16,8,true>(c, x, y);
-            case 4: return mass_launch_v<NC,WITH_DEN,8,8,true>(c, x, y);
+            case 4: return mass_launch_v<NC,WITH_DEN,32,2>(c, x, y);
          }
+         return mass_launch_v<NC,WITH_DEN,8,8,true>(c, x, y);
       }
       return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3>(c, x, y);
    }
@@ -92,9 +93,9 @@ struct TunedLaunch3D
          {
             case 1: return qupdate_launch<2>(c, S, prm);
             case 2: return qupdate_launch<1>(c, S, prm);
-            case 3: return qupdate_launch<4>(c, S, prm);
+            case 3: return qupdate_launch<3>(c, S, prm);
          }
-         return qupdate_launch<3>(c, S, prm);   // 3 CTAs/SM (80 registers, small L1-resident spill) beats 2 CTAs at 128
+         return qupdate_launch<4>(c, S, prm);   // 4 CTAs/SM (72 registers, L1-resident spill) beat 2 CTAs at 128: 8.1 vs 9.9 ms
       }
       if (Q1D >= 10 || c.tune[2] == 1) { return qupdate_launch<1>(c, S, prm); }   // Q1D = 10: one CTA per SM by shared memory
       return qupdate_launch<2>(c, S, prm);
