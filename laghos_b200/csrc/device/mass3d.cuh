@@ -41,7 +41,7 @@ struct Mass3DCfg
    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*ND*sizeof(int);
 };
 
-template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_SCATTER>
+template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_SCATTER, bool DIRECT_GATHER = false>
 __global__ void __launch_bounds__(((NC*NB*D1D + 31)/32)*32, MINB)
 mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t cstride,
        const int *__restrict__ map, const double *__restrict__ Dq,
@@ -76,6 +76,12 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
    // ---- phase 0: cooperative gather, lanes along the element-local dof index (runs of D1D
    //      contiguous L-vector entries per lattice row).  Slice (c,e,dz) is parked in the
    //      first DD slots of its own plane.
+   if (DIRECT_GATHER)
+   {
+      // only the restriction indices are staged; each slice thread gathers its own DD values
+      for (int it = t; it < nel*C::ND; it += C::T) { sIdx[it] = __ldg(map + (size_t)eb*C::ND + it); }
+   }
+   else
    {
       // all index loads first, then all value loads (independent requests in flight), then the stores
       constexpr int NIT = (NB*C::ND + C::T - 1)/C::T;
@@ -114,13 +120,21 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
    // ---- phase A: x then y contraction of the slice, store plane ----
    if (active)
    {
+      double XG[DIRECT_GATHER ? C::DD : 1];
+      if (DIRECT_GATHER)
+      {
+         const int *ids = sIdx + e_loc*C::ND + dz*C::DD;
+         const double *xc = x + (size_t)c*cstride;
+#pragma unroll
+         for (int i = 0; i < C::DD; i++) { XG[i] = xc[ids[i]]; }
+      }
       double U[Q1D][D1D];
 #pragma unroll
       for (int dy = 0; dy < D1D; dy++)
       {
          double X[D1D];
 #pragma unroll
-         for (int dx = 0; dx < D1D; dx++) { X[dx] = pl[dx + D1D*dy]; }
+         for (int dx = 0; dx < D1D; dx++) { X[dx] = DIRECT_GATHER ? XG[dx + D1D*dy] : pl[dx + D1D*dy]; }
 #pragma unroll
          for (int qx = 0; qx < Q1D; qx++)
          {

@@ -23,11 +23,11 @@ struct TunedLaunch3D
    using Tab = DevTables<D1D,Q1D>;
    static const Tab &tab(Ctx &c) { return *reinterpret_cast<const Tab*>(c.tab_blob.data()); }
 
-   template<int NC, bool WITH_DEN, int NB, int MINB, bool DS = false>
+   template<int NC, bool WITH_DEN, int NB, int MINB, bool DS = false, bool DG = false>
    static int mass_launch_v(Ctx &c, const double *x, double *y)
    {
       using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
-      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB,DS>;
+      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB,DS,DG>;
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
       const int grid = (c.NE + NB - 1)/NB;
@@ -44,8 +44,8 @@ struct TunedLaunch3D
       {
          switch (c.tune[0])
          {
-            case 1: return mass_launch_v<NC,WITH_DEN,8,7,true>(c, x, y);
-            case 2: return mass_launch_v<NC,WITH_DEN,4,12,true>(c, x, y);
+            case 1: return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);
+            case 2: return mass_launch_v<NC,WITH_DEN,16,3,true,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
          }
