@@ -44,12 +44,12 @@ struct TunedLaunch3D
       {
          switch (c.tune[0])
          {
-            case 1: return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);
+            case 1: return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);
             case 2: return mass_launch_v<NC,WITH_DEN,16,3,true,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
          }
-         return mass_launch_v<NC,WITH_DEN,8,6,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants.txt)
+         return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants*.txt): 351 us
       }
       if constexpr (NC == 1 && D1D == 4)   // single-component apply (lagb_tune_set key 3)
       {
@@ -60,9 +60,10 @@ struct TunedLaunch3D
             case 3: return mass_launch_v<NC,WITH_DEN,16,8,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,32,2>(c, x, y);
          }
-         return mass_launch_v<NC,WITH_DEN,8,8,true>(c, x, y);
+         return mass_launch_v<NC,WITH_DEN,8,8,true,true>(c, x, y);
       }
-      return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3>(c, x, y);
+      // direct gather / scatter for the low orders; staged through shared memory where registers are tight
+      return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3,(D1D <= 3),(D1D <= 3)>(c, x, y);
    }
    static int mass_h1(Ctx &c, int nc, const double *x, double *y, bool with_den)
    {
