@@ -432,9 +432,6 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    rc |= dev_alloc(&c.d_lz, (size_t)c.ndofs_l2);
    c.part_cap = std::max(c.NE, 148*16)*4 + 64;
    rc |= dev_alloc(&c.d_part, (size_t)c.part_cap);
-   c.ticket_cap = c.NE/64 + 64;
-   rc |= dev_alloc(&c.d_ticket, (size_t)c.ticket_cap);
-   if (!rc) { LAGB_CUDA(cudaMemset(c.d_ticket, 0, sizeof(unsigned int)*c.ticket_cap)); }
    rc |= dev_alloc(&c.d_tmp, 16); rc |= dev_alloc(&c.d_dt, 1); rc |= dev_alloc(&c.d_elem_vol, (size_t)c.NE);
    rc |= dev_alloc(&c.d_state, 1);
    if (rc) { lagb_ctx_destroy(h); return LAGB_ERR_CUDA; }
@@ -452,7 +449,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    cudaStreamSynchronize(c.stream);
    void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_inv_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
                    c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinv, c.d_essmask, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
-                   c.d_part, c.d_ticket, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
+                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
    void *hp[] = {c.d_pack_idx, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_send_all, c.d_recv_all};

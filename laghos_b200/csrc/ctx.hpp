@@ -61,7 +61,6 @@ struct Ctx
    double *d_r = nullptr, *d_d = nullptr, *d_z = nullptr;      // [dim*ndofs]
    double *d_lr = nullptr, *d_ld = nullptr, *d_lz = nullptr;   // [ndofs_l2]
    double *d_part = nullptr; int part_cap = 0;                 // reduction partials
-   unsigned int *d_ticket = nullptr; int ticket_cap = 0;       // arrival counters of the in-kernel group reductions (self-resetting)
    double *d_tmp = nullptr;                                    // [8] reduced scalars
    double *d_dt = nullptr;                                     // [1]
    double *d_elem_vol = nullptr;

@@ -45,8 +45,7 @@ template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_
 __global__ void __launch_bounds__(((NC*NB*D1D + 31)/32)*32, MINB)
 mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t cstride,
        const int *__restrict__ map, const double *__restrict__ Dq,
-       const double *__restrict__ x, double *__restrict__ y, double *__restrict__ den_part,
-       unsigned int *__restrict__ den_ticket)
+       const double *__restrict__ x, double *__restrict__ y, double *__restrict__ den_part)
 {
    using C = Mass3DCfg<D1D,Q1D,NB,NC>;
    extern __shared__ double sV[];   // [c][e_loc][dz][PLANE]
@@ -284,36 +283,11 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
          if ((t & 31) == 0) { red[cc*NW + (t >> 5)] = v; }
       }
       __syncthreads();
-      // Two-level fixed-order reduction without a second kernel: CTA partials are grouped by
-      // DEN_GROUP consecutive CTAs; the last CTA of a group to arrive (ticket) sums the group's
-      // partials in index order into den_part[group] (stored after the per-CTA slots).  The
-      // finish kernel then adds ngroups values instead of grid values.
-      constexpr int DEN_GROUP = 64;
-      const int grid = gridDim.x, group = blockIdx.x / DEN_GROUP;
-      const int gsize = min(DEN_GROUP, grid - group*DEN_GROUP);
-      double *cta_part = den_part + (size_t)((grid + DEN_GROUP - 1)/DEN_GROUP)*NC;   // [grid][NC] after [ngroups][NC]
       if (t < NC)
       {
          double s = 0.0;
          for (int w = 0; w < NW; w++) { s += red[t*NW + w]; }
-         cta_part[(size_t)blockIdx.x*NC + t] = s;
-         __threadfence();
-      }
-      __syncthreads();
-      __shared__ bool am_last;
-      if (t == 0) { am_last = (atomicAdd(&den_ticket[group], 1u) == (unsigned int)(gsize - 1)); }
-      __syncthreads();
-      if (am_last)
-      {
-         __threadfence();
-         if (t < NC)
-         {
-            const volatile double *p = cta_part + (size_t)group*DEN_GROUP*NC + t;
-            double s = 0.0;
-            for (int b = 0; b < gsize; b++) { s += p[(size_t)b*NC]; }
-            den_part[(size_t)group*NC + t] = s;
-         }
-         if (t == 0) { den_ticket[group] = 0u; }   // self-resetting for the next launch
+         den_part[(size_t)blockIdx.x*NC + t] = s;
       }
    }
 }

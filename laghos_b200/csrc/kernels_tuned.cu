@@ -30,12 +30,11 @@ struct TunedLaunch3D
       auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB,DS,DG>;
       static bool attr_set = false;
       if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
-      const int grid = (c.NE + NB - 1)/NB, ngroups = (grid + 63)/64;
-      if (WITH_DEN && (grid + ngroups)*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
-      if (WITH_DEN && ngroups > c.ticket_cap) { set_error("mass3d: ticket buffer too small"); return LAGB_ERR_STATE; }
-      kern<<<grid, Cfg::T, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part, c.d_ticket);
+      const int grid = (c.NE + NB - 1)/NB;
+      if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
+      kern<<<grid, Cfg::T, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part);
       LAGB_LAUNCH_CHECK();
-      if (WITH_DEN) { c.dt_nblocks = ngroups; }   // the kernel leaves one fixed-order partial per group of 64 CTAs
+      if (WITH_DEN) { c.dt_nblocks = grid; }
       return LAGB_OK;
    }
    template<int NC, bool WITH_DEN>
