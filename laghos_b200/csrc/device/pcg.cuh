@@ -130,7 +130,7 @@ __global__ void reduce_partials(int nblocks, const double *__restrict__ part, do
 // Fixed-order reduction of part[b*NC + c], b < nblocks, by one block of FB threads: thread t
 // sums b = t, t+FB, ... (4 independent partial sums keep the loads in flight), then a
 // shuffle/shared tree.  Result valid on thread 0.
-constexpr int FB = 512;
+constexpr int FB = 1024;
 template<int NC>
 __device__ __forceinline__ void reduce_to_thread0(const double *__restrict__ part, int nblocks, double *out, double *sh)
 {

@@ -346,6 +346,42 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
       __syncthreads();
    }
    // z pencils (e, c, g, column): W[c][g][dz][col] = sum_qz Tz(qz,dz) sJit(q,g,c) Eq(q), Tz = G for g == 2
+   if (NB == 1 && !PREFETCH)
+   {
+      // one element per CTA: every stressJinvT load of the thread is issued before the first
+      // dependent instruction (all rounds unrolled): memory-level parallelism for the HBM stream
+      constexpr int NR = (9*QQ + NT - 1)/NT;
+      double sv[NR][Q1D];
+#pragma unroll
+      for (int k = 0; k < NR; k++)
+      {
+         const int r = tid + k*NT;
+         if (r < 9*QQ)
+         {
+            const int col = r % QQ, cg = r / QQ;
+            const double *s = sJit + (size_t)eb*C::NQ + NEQ*cg + col;
+#pragma unroll
+            for (int qz = 0; qz < Q1D; qz++) { sv[k][qz] = __ldg(s + QQ*qz); }
+         }
+      }
+#pragma unroll
+      for (int k = 0; k < NR; k++)
+      {
+         const int r = tid + k*NT;
+         if (r < 9*QQ)
+         {
+            const int col = r % QQ, cg = r / QQ;
+            double w[D1D];
+#pragma unroll
+            for (int qz = 0; qz < Q1D; qz++) { sv[k][qz] *= Eq[col + QQ*qz]; }
+            if (cg % 3 == 2) { pencil_bwd<D1D,Q1D>(tab.G, sv[k], w); }
+            else { pencil_bwd<D1D,Q1D>(tab.B, sv[k], w); }
+#pragma unroll
+            for (int dz = 0; dz < D1D; dz++) { W[col + QQ*(dz + D1D*cg)] = w[dz]; }
+         }
+      }
+   }
+   else
    for (int it = tid; it < nel*9*QQ; it += NT)
    {
       const int e = it / (9*QQ), r = it - e*(9*QQ);

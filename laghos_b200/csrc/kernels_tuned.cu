@@ -131,10 +131,10 @@ struct TunedLaunch3D
       {
          switch (c.tune[1])
          {
-            case 1: return force_launch<1,64,true>(c, e, v);
+            case 1: return force_launch<1,96>(c, e, v);
             case 2: return force_launch<4,256>(c, e, v);
-            case 3: return force_launch<1,96,true>(c, e, v);
-            case 4: return force_launch<2,128,true>(c, e, v);
+            case 3: return force_launch<1,128>(c, e, v);
+            case 4: return force_launch<1,192>(c, e, v);
          }
       }
       return force_launch<NBF,NTF>(c, e, v);
