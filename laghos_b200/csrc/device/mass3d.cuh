@@ -38,7 +38,8 @@ struct Mass3DCfg
    static constexpr bool PREFETCH = (NCOL*Q1D <= 24); // hold the columns' D values in registers across phase A
    static constexpr int PLANE = ((QQ > DD ? QQ : DD) | 1);   // plane stride (odd: conflict-free 64-bit)
    static constexpr int SMEM_DOUBLES = NC*NB*D1D*PLANE;
-   static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*ND*sizeof(int);
+   static constexpr int IDXS = DD | 1;              // padded index stride per slice (odd: lanes = slices read conflict-free)
+   static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*D1D*IDXS*sizeof(int);
 };
 
 template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_SCATTER, bool DIRECT_GATHER = false>
@@ -49,7 +50,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
 {
    using C = Mass3DCfg<D1D,Q1D,NB,NC>;
    extern __shared__ double sV[];   // [c][e_loc][dz][PLANE]
-   int *sIdx = reinterpret_cast<int*>(sV + C::SMEM_DOUBLES);   // [e_loc][ND]
+   int *sIdx = reinterpret_cast<int*>(sV + C::SMEM_DOUBLES);   // [e_loc][dz][IDXS]
    const int t = threadIdx.x;
    const int c = t / C::TG, r = t - c*C::TG;
    const int e_loc = r / D1D, dz = r % D1D;
@@ -79,7 +80,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
    if (DIRECT_GATHER)
    {
       // only the restriction indices are staged; each slice thread gathers its own DD values
-      for (int it = t; it < nel*C::ND; it += C::T) { sIdx[it] = __ldg(map + (size_t)eb*C::ND + it); }
+      for (int it = t; it < nel*C::ND; it += C::T) { sIdx[(it / C::DD)*C::IDXS + it % C::DD] = __ldg(map + (size_t)eb*C::ND + it); }
    }
    else
    {
@@ -109,7 +110,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
          {
             const int e2 = it / C::ND, i = it - e2*C::ND;
             const int z = i / C::DD, ixy = i - z*C::DD;
-            sIdx[it] = id[k];
+            sIdx[(it / C::DD)*C::IDXS + it % C::DD] = id[k];
 #pragma unroll
             for (int cc = 0; cc < NC; cc++) { sV[((size_t)(cc*NB + e2)*D1D + z)*C::PLANE + ixy] = xv[k][cc]; }
          }
@@ -123,7 +124,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
       double XG[DIRECT_GATHER ? C::DD : 1];
       if (DIRECT_GATHER)
       {
-         const int *ids = sIdx + e_loc*C::ND + dz*C::DD;
+         const int *ids = sIdx + (e_loc*D1D + dz)*C::IDXS;
          const double *xc = x + (size_t)c*cstride;
 #pragma unroll
          for (int i = 0; i < C::DD; i++) { XG[i] = xc[ids[i]]; }
@@ -225,7 +226,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
       if (DIRECT_SCATTER)
       {
          // scatter-add straight from registers (restriction indices of the slice from smem)
-         const int *ids = sIdx + e_loc*C::ND + dz*C::DD;
+         const int *ids = sIdx + (e_loc*D1D + dz)*C::IDXS;
          double *yc = y + (size_t)c*cstride;
 #pragma unroll
          for (int dy = 0; dy < D1D; dy++)
@@ -260,7 +261,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
       for (int it = t; it < nel*C::ND; it += C::T)
       {
          const int e2 = it / C::ND, i = it - e2*C::ND;
-         const int id = sIdx[it];
+         const int id = sIdx[(it / C::DD)*C::IDXS + it % C::DD];
          const int z = i / C::DD, ixy = i - z*C::DD;
 #pragma unroll
          for (int cc = 0; cc < NC; cc++)
