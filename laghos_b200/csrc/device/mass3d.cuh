@@ -38,7 +38,9 @@ struct Mass3DCfg
    static constexpr bool PREFETCH = (NCOL*Q1D <= 24); // hold the columns' D values in registers across phase A
    static constexpr int PLANE = ((QQ > DD ? QQ : DD) | 1);   // plane stride (odd: conflict-free 64-bit)
    static constexpr int SMEM_DOUBLES = NC*NB*D1D*PLANE;
-   static constexpr int IDXS = DD | 1;              // padded index stride per slice (odd: lanes = slices read conflict-free)
+   // index stride per slice: odd (conflict-free scalar reads, lanes = slices) for the batched
+   // apply; dense for one component, where 128-bit index loads measured faster (187 vs 210 us)
+   static constexpr int IDXS = (NC == 1) ? DD : (DD | 1);
    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*D1D*IDXS*sizeof(int);
 };
 
