@@ -6,19 +6,20 @@
 //   * NC*D1D threads per element, NB elements per CTA, NC velocity components per pass
 //     (NC = 3 in the batched PCG: the quadrature data D is read ONCE for all three
 //     component solves of SolveVelocity, laghos_solver.cpp:363-398).
-//   * phase 0  all threads gather the CTA's element dofs with lanes along the element-local
-//              dof index (4x fewer L1 sectors per request than a per-slice gather);
-//   * phase A  thread (c,e,dz) contracts x then y of slice dz of component c in registers
+//   * the D values of the thread's phase-B columns are requested first (registers) so that
+//     their DRAM latency overlaps the gather and phase A;
+//   * phase 0  the CTA's restriction indices are staged in shared memory (and, in the staged
+//              variant DIRECT_GATHER = false, the dof values too, lanes along the dof index);
+//   * phase A  thread (c,e,dz) gathers slice dz of component c, contracts x then y in registers
 //              (B in the kernel-parameter constant bank, fully unrolled) and stores the
 //              Q1D^2 plane to shared memory;
 //   * phase B  flat (element,column) index over the CTA's NB*Q1D^2 quadrature columns:
-//              contract z (D1D -> Q1D), scale by D (coalesced streaming loads, each byte
-//              of D touched once), contract z back (Q1D -> D1D), in registers, in place
-//              in shared memory; optionally accumulates d^t A d = sum_q D u_q^2 for the
+//              contract z (D1D -> Q1D), scale by D, contract z back (Q1D -> D1D), in registers,
+//              in place in shared memory; optionally accumulates d^t A d = sum_q D u_q^2 for the
 //              PCG denominator at no extra memory traffic;
-//   * phase C  thread (c,e,dz) contracts y then x back to dofs;
-//   * phase D  all threads scatter-add to the L-vector (red.global.add.f64), lanes along the
-//              dof index so that the D1D entries of a lattice row share one L2 sector.
+//   * phase C  thread (c,e,dz) contracts y then x back to dofs and scatter-adds them
+//              (red.global.add.f64) straight from registers (DIRECT_SCATTER) or through a
+//              cooperative phase D with lanes along the dof index.
 //   Shared memory traffic is 4*D1D*Q1D^2 doubles per element and component (no
 //   per-FMA shared operands); every thread is active in every phase.
 #pragma once
