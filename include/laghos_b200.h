@@ -192,6 +192,14 @@ int lagb_dev_free(lagb_ctx *ctx, double *d_ptr);
 int lagb_memcpy_h2d(lagb_ctx *ctx, double *d_dst, const double *h_src, int64_t n);        /* synchronous */
 int lagb_memcpy_h2d_async(lagb_ctx *ctx, double *d_dst, const double *h_src, int64_t n);
 int lagb_memcpy_d2h(lagb_ctx *ctx, double *h_dst, const double *d_src, int64_t n);        /* synchronous */
+/* Pipelined state transfers (bench e2e): copies run on the context's COPY stream and overlap the
+ * compute stream.  lagb_memcpy_h2d_bg: the copy starts once the compute work enqueued so far has
+ * finished (it overwrites d_dst) and after earlier background copies; kernels that read d_dst must be
+ * preceded by lagb_wait_copies.  lagb_memcpy_d2h_bg: the copy starts once the compute work enqueued
+ * so far has finished; h_dst is valid after lagb_ctx_sync (which also drains the copy stream). */
+int lagb_memcpy_h2d_bg(lagb_ctx *ctx, double *d_dst, const double *h_src, int64_t n);
+int lagb_memcpy_d2h_bg(lagb_ctx *ctx, double *h_dst, const double *d_src, int64_t n);
+int lagb_wait_copies(lagb_ctx *ctx);   /* the compute stream waits for the background copies enqueued so far */
 int lagb_host_alloc_pinned(double **h_out, int64_t n);
 int lagb_host_free_pinned(double *h_ptr);
 

@@ -66,7 +66,7 @@ lagb_ctx_create lagb_ctx_destroy lagb_ctx_sync lagb_setup_qdata0 lagb_vmass_mult
 lagb_emass_mult lagb_force_mult lagb_force_mult_transpose lagb_qupdate lagb_dt_est_set
 lagb_qupdate_async lagb_dt_est_read lagb_pcg_vmass lagb_pcg_vmass_all lagb_cg_emass lagb_taylor_source
 lagb_qdata_ptr lagb_qdata_h0 lagb_qdata_set_h0 lagb_dev_malloc lagb_dev_free lagb_memcpy_h2d
-lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_host_alloc_pinned lagb_host_free_pinned lagb_vec_fill
+lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_memcpy_h2d_bg lagb_memcpy_d2h_bg lagb_wait_copies lagb_host_alloc_pinned lagb_host_free_pinned lagb_vec_fill
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
 lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set""".split()

@@ -435,6 +435,9 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    rc |= dev_alloc(&c.d_tmp, 16); rc |= dev_alloc(&c.d_dt, 1); rc |= dev_alloc(&c.d_elem_vol, (size_t)c.NE);
    rc |= dev_alloc(&c.d_state, 1);
    if (rc) { lagb_ctx_destroy(h); return LAGB_ERR_CUDA; }
+   LAGB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+   LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
+   LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
    LAGB_CUDA(cudaMallocHost((void**)&c.h_state, sizeof(pcg::State)));
    LAGB_CUDA(cudaMallocHost((void**)&c.h_scal, 16*sizeof(double)));
    LAGB_CUDA(cudaMemset(c.d_sJit, 0, NEQ*D2*sizeof(double)));
@@ -454,6 +457,9 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
    void *hp[] = {c.d_pack_idx, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_send_all, c.d_recv_all};
    for (void *p : hp) { if (p) { cudaFree(p); } }
+   if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); }
+   if (c.ev_compute) { cudaEventDestroy(c.ev_compute); }
+   if (c.ev_copy) { cudaEventDestroy(c.ev_copy); }
    if (c.h_state) { cudaFreeHost(c.h_state); }
    if (c.h_scal) { cudaFreeHost(c.h_scal); }
    for (int w = 0; w < Timer::NT; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
@@ -462,7 +468,12 @@ void lagb_ctx_destroy(lagb_ctx *h)
    delete h;
 }
 
-int lagb_ctx_sync(lagb_ctx *h) { LAGB_CUDA(cudaStreamSynchronize(h->c.stream)); return LAGB_OK; }
+int lagb_ctx_sync(lagb_ctx *h)
+{
+   LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
+   if (h->c.copy_stream) { LAGB_CUDA(cudaStreamSynchronize(h->c.copy_stream)); }
+   return LAGB_OK;
+}
 
 int lagb_setup_qdata0(lagb_ctx *h, const double *d_x0, const double *d_rho0_gf, const double *d_rho0_q,
                       int64_t ne_global, double *h0_out)
@@ -694,6 +705,30 @@ int lagb_memcpy_d2h(lagb_ctx *h, double *h_dst, const double *d_src, int64_t n)
 {
    LAGB_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double)*n, cudaMemcpyDeviceToHost, h->c.stream));
    LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
+   return LAGB_OK;
+}
+int lagb_memcpy_h2d_bg(lagb_ctx *h, double *d_dst, const double *h_src, int64_t n)
+{
+   Ctx &c = h->c;
+   LAGB_CUDA(cudaEventRecord(c.ev_compute, c.stream));
+   LAGB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_compute, 0));
+   LAGB_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double)*n, cudaMemcpyHostToDevice, c.copy_stream));
+   LAGB_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+   return LAGB_OK;
+}
+int lagb_memcpy_d2h_bg(lagb_ctx *h, double *h_dst, const double *d_src, int64_t n)
+{
+   Ctx &c = h->c;
+   LAGB_CUDA(cudaEventRecord(c.ev_compute, c.stream));
+   LAGB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_compute, 0));
+   LAGB_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double)*n, cudaMemcpyDeviceToHost, c.copy_stream));
+   LAGB_CUDA(cudaEventRecord(c.ev_copy, c.copy_stream));
+   return LAGB_OK;
+}
+int lagb_wait_copies(lagb_ctx *h)
+{
+   Ctx &c = h->c;
+   LAGB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
    return LAGB_OK;
 }
 int lagb_host_alloc_pinned(double **h_out, int64_t n)

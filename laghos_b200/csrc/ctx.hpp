@@ -50,6 +50,8 @@ struct Ctx
    int64_t ndofs = 0, ndofs_l2 = 0;
    int use_visc = 1, use_vort = 0, variant = 0, device = 0;
    cudaStream_t stream = nullptr;
+   cudaStream_t copy_stream = nullptr;               // background state transfers (lagb_memcpy_*_bg)
+   cudaEvent_t ev_compute = nullptr, ev_copy = nullptr;
    KernelSet ks, ks_generic;
    std::vector<unsigned char> tab_blob;   // DevTables<D1D,Q1D> bytes
    // device arrays

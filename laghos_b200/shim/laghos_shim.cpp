@@ -72,8 +72,12 @@ void LagrangianHydroOperator::Mult(const Vector &S, Vector &dS_dt) const
    Vector v, dx;
    v.MakeRef(S, H1Vsize, H1Vsize);
    dx.MakeRef(dS_dt, 0, H1Vsize);
-   dx = v;
+   // reference order is dx = v; SolveVelocity; SolveEnergy (laghos_solver.cpp:316-325).  dx and dv are
+   // disjoint slices of dS_dt, so dx = v may follow SolveVelocity: with current quadrature data
+   // SolveVelocity does not read S, which lets a background H2D copy of S overlap Force + PCG.
    SolveVelocity(S, dS_dt);
+   WaitState();
+   dx = v;
    SolveEnergy(S, v, dS_dt);
    qdata_is_current = false;
 }
@@ -82,6 +86,7 @@ void LagrangianHydroOperator::UpdateQuadratureData(const Vector &S) const
 {
    if (qdata_is_current) { return; }
    qdata_is_current = true;
+   WaitState();
    qupdate.UpdateQuadratureData(S, qdata);
 }
 
@@ -262,6 +267,7 @@ void RK2AvgSolver::Step(Vector &S, double &t, double &dt)
       S0.SetSize(S.Ctx(), S.Size()); dS_dt.SetSize(S.Ctx(), S.Size()); V.SetSize(S.Ctx(), NV);
       dS_dt = 0.0;
    }
+   hydro_oper->WaitState();   // S may still be arriving from the host (bench e2e)
    S0 = S;
    Vector v0, dx_dt, dv_dt;
    v0.MakeRef(S0, NV, NV); dx_dt.MakeRef(dS_dt, 0, NV); dv_dt.MakeRef(dS_dt, NV, NV);
@@ -393,8 +399,15 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
       {
          if (t + dt >= opt->t_final) { dt = opt->t_final - t; last_step = true; }
          if (steps == opt->max_tsteps) { last_step = true; }
-         if (opt->e2e_host_state) { LAGHOS_CHECK(lagb_memcpy_h2d_async(ctx, S.Write(), S_pin, N)); }
-         S_old = S;
+         if (opt->e2e_host_state)
+         {
+            // S comes from pinned host memory every step; the copy runs on the copy stream behind the
+            // previous step's D2H and overlaps the first Force + PCG of the step (which do not read S).
+            // The host copy doubles as the rollback state (it is only overwritten by accepted steps).
+            LAGHOS_CHECK(lagb_memcpy_h2d_bg(ctx, S.Write(), S_pin, N));
+            hydro.StatePending();
+         }
+         else { S_old = S; }
          t_old = t;
          hydro.ResetTimeStepEstimate();
          ode_solver->Step(S, t, dt);
@@ -405,7 +418,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
             dt *= 0.85;
             if (dt < std::numeric_limits<double>::epsilon()) { LAGHOS_ABORT("The time step crashed!"); }
             t = t_old;
-            S = S_old;
+            if (!opt->e2e_host_state) { S = S_old; }   // e2e: the next iteration reloads S from the host copy
             hydro.ResetQuadratureData();
             if (opt->verbose && opt->rank == 0) { printf("Repeating step %d\n", ti); }
             if (steps < opt->max_tsteps) { last_step = false; }
@@ -414,7 +427,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          else
          {
             if (dt_est > 1.25*dt) { dt *= 1.02; }
-            if (opt->e2e_host_state) { LAGHOS_CHECK(lagb_memcpy_d2h(ctx, S_pin, S.Read(), N)); }
+            if (opt->e2e_host_state) { LAGHOS_CHECK(lagb_memcpy_d2h_bg(ctx, S_pin, S.Read(), N)); }   // overlaps the next step's start
             const bool print = opt->verbose && (last_step || (ti % std::max(1, opt->vis_steps)) == 0);
             if (hist_cap > 0 || print || last_step)
             {
@@ -433,6 +446,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          }
       }
       if (!sw_started) { LAGHOS_CHECK(lagb_stopwatch_start(ctx)); }
+      if (opt->e2e_host_state) { LAGHOS_CHECK(lagb_wait_copies(ctx)); }   // the timed region ends after the last D2H
       LAGHOS_CHECK(lagb_stopwatch_stop(ctx, &res->device_seconds));
       const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wall0).count();
       LAGHOS_CHECK(lagb_profile_mass_get(ctx, &res->mass_kernel_seconds, &res->mass_kernel_launches));

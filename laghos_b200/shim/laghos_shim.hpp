@@ -177,6 +177,7 @@ protected:
    bool batched_pcg;
    mutable QuadratureData qdata;
    mutable bool qdata_is_current = false;
+   mutable bool state_pending = false;   // a background H2D copy of S is in flight (bench e2e): wait before the first read
    ForcePAOperator *ForcePA;
    MassPAOperator *VMassPA, *EMassPA;
    mutable CGSolver CG_VMass, CG_EMass;
@@ -192,6 +193,8 @@ public:
    double GetTimeStepEstimate(const Vector &S) const;
    void ResetTimeStepEstimate() const;
    void ResetQuadratureData() const { qdata_is_current = false; }
+   void StatePending() const { state_pending = true; }
+   void WaitState() const { if (state_pending) { LAGHOS_CHECK(lagb_wait_copies(ctx)); state_pending = false; } }
    void UpdateQuadratureData(const Vector &S) const;
    int64_t GetH1VSize() const { return H1Vsize; }
    // reference PrintTimingData (laghos_solver.cpp:699-796): fom[0]=total, 1=CG(H1), 2=forces, 3=qdata, 4=T_total
