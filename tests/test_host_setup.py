@@ -55,3 +55,56 @@ def test_partition_consistency(built, pgrid):
             xo = parts[nr].S0[:parts[nr].h1_vsize].reshape(3, -1)
             assert np.allclose(xl[:, dofs], xo[:, back[0]], atol=0)
     assert abs(sum(np.abs(p.S0[2 * p.h1_vsize:]).sum() for p in parts) - np.abs(G.S0[2 * G.h1_vsize:]).sum()) < 1e-12
+
+
+@pytest.mark.parametrize("pgrid", [(2, 2, 2), (2, 2, 1), (3, 1, 2)])
+def test_partition_single_phase_sum(built, pgrid):
+    """Emulate the single-phase shared-dof exchange (capi.cu halo_pack_all / halo_combine) in numpy for
+    every rank of a process grid: each rank adds the values received from ALL its sharers (faces,
+    edges, corners) in ascending rank order.  Every copy of a shared dof must end up with the same
+    value, equal to the globally assembled sum."""
+    from laghos_b200.api import Problem
+    mesh, rs, ok, ot = "cube01_hex", 1, 2, 1
+    G = Problem(mesh, rs, 1, ok, ot)
+    n = pgrid[0] * pgrid[1] * pgrid[2]
+    parts = [Problem(mesh, rs, 1, ok, ot, rank=r, pgrid=pgrid) for r in range(n)]
+    xg = G.S0[:G.h1_vsize].reshape(3, -1)
+    key = {tuple(np.round(xg[:, i], 12)): i for i in range(G.ndofs_h1)}
+    l2g = []
+    for p in parts:
+        xl = p.S0[:p.h1_vsize].reshape(3, -1)
+        l2g.append(np.array([key[tuple(np.round(xl[:, i], 12))] for i in range(p.ndofs_h1)]))
+    rng = np.random.default_rng(3)
+    local = [rng.uniform(-1, 1, p.ndofs_h1) for p in parts]
+    assembled = np.zeros(G.ndofs_h1)
+    for r in range(n):
+        np.add.at(assembled, l2g[r], local[r])
+    nbrs = [p.neighbours() for p in parts]
+    out = []
+    for r in range(n):
+        contrib = {}   # dof -> [(rank, value)]
+        for (nr, ph, dofs) in nbrs[r]:
+            assert ph == 0
+            back = [d for (rr, pp, d) in nbrs[nr] if rr == r]
+            assert len(back) == 1 and len(back[0]) == len(dofs)
+            for mine, theirs in zip(dofs, back[0]):
+                contrib.setdefault(int(mine), []).append((nr, local[nr][theirs]))
+        v = local[r].copy()
+        for dof, lst in contrib.items():
+            lst.append((r, local[r][dof]))
+            acc = 0.0
+            for _, val in sorted(lst):
+                acc += val
+            v[dof] = acc
+        out.append(v)
+    for r in range(n):
+        assert np.allclose(out[r], assembled[l2g[r]], rtol=0, atol=1e-14)
+    # bit-identical copies of every shared dof across ranks (rank-ordered summation)
+    owner_val = {}
+    for r in range(n):
+        for i, g in enumerate(l2g[r]):
+            if g in owner_val:
+                assert owner_val[g] == out[r][i]
+            else:
+                owner_val[g] = out[r][i]
+    assert sum(int(p.owner_mask.sum()) for p in parts) == G.ndofs_h1
