@@ -365,21 +365,5 @@ static __global__ void vec_zero_idx(double *__restrict__ y, const int *__restric
 {
    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) { y[idx[i]] = 0.0; }
 }
-// inout[0] = min(inout[0], min_i part[i])
-static __global__ void vec_min_reduce(int n, const double *__restrict__ part, double *__restrict__ out)
-{
-   __shared__ double sh[32];
-   double m = out[0];
-   for (int i = threadIdx.x; i < n; i += blockDim.x) { m = fmin(m, part[i]); }
-   for (int o = 16; o > 0; o >>= 1) { m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o)); }
-   if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = m; }
-   __syncthreads();
-   if (threadIdx.x == 0)
-   {
-      for (int w = 1; w < (blockDim.x + 31)/32; w++) { m = fmin(m, sh[w]); }
-      out[0] = m;
-   }
-}
-
 } // namespace pcg
 } // namespace lagb
