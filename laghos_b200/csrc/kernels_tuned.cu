@@ -95,6 +95,7 @@ struct TunedLaunch3D
             case 1: return qupdate_launch<2>(c, S, prm);
             case 2: return qupdate_launch<1>(c, S, prm);
             case 3: return qupdate_launch<3>(c, S, prm);
+            case 4: return qupdate_launch<5>(c, S, prm);
          }
          return qupdate_launch<4>(c, S, prm);   // 4 CTAs/SM (72 registers, L1-resident spill) beat 2 CTAs at 128: 8.1 vs 9.9 ms
       }
