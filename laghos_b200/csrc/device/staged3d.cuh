@@ -200,8 +200,8 @@ struct QUpd3DCfg
    static constexpr int S_DOF = NF*ND + NL;
    // dofs alias the stage-2 arrays (dead after the x pencils)
    static constexpr int S_A = (3*S_ST2 > S_DOF) ? 3*S_ST2 : S_DOF;
-   static constexpr int S_TAB = 2*Q1D*D1D;                 // B, G for the per-point z pass (runtime qz)
-   static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + NQ + 32 + S_TAB;
+   static constexpr int S_TAB = 2*Q1D*D1D + Q1D*L1D;       // B, G, BL for the per-point z pass (runtime qz)
+   static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + 32 + S_TAB;
    static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES;
 };
 
@@ -218,12 +218,13 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
    extern __shared__ double smem[];
    double *A = smem;                            // dofs, later BB | GB | BG
    double *Bx = A + C::S_A, *Gx = Bx + C::S_ST1;
-   double *E1 = Gx + C::S_ST1, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2, *red = Eq + C::NQ;
-   double *TB = red + 32, *TG = TB + Q1D*D1D;
+   double *E1 = Gx + C::S_ST1, *E2 = E1 + C::S_E1, *red = E2 + C::S_E2;
+   double *TB = red + 32, *TG = TB + Q1D*D1D, *TBL = TG + Q1D*D1D;
    const int tid = threadIdx.x;
    const int e = blockIdx.x;
    const size_t NEQ = (size_t)NE*C::NQ;
    for (int i = tid; i < Q1D*D1D; i += NT) { TB[i] = tab.B[i]; TG[i] = tab.G[i]; }
+   for (int i = tid; i < Q1D*C::L1D; i += NT) { TBL[i] = tab.BL[i]; }
    // gather x, v (6 scalar fields: S = (x | v | e), field f at offset f*ndofs) and e
    {
       const double *en = S + 6*ndofs;
@@ -236,9 +237,76 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
       for (int it = tid; it < C::NL; it += NT) { A[C::NF*C::ND + it] = en[(size_t)e*C::NL + it]; }
    }
    __syncthreads();
-   l2_values<C::L1D,Q1D>(tab.BL, 1, A + C::NF*C::ND, 0, E1, 0, E2, 0, Eq, 0, tid, NT);
+   // Two merged pencil stages (H1 gradient of the 6 fields + L2 interpolation of e) instead of five:
+   // every barrier of a one-element CTA costs the latency tail of its slowest warp.
    double *BB = A, *GB = A + C::S_ST2, *BG = A + 2*C::S_ST2;
-   grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, 1, A, 0, Bx, Gx, 0, BB, GB, BG, 0, tid, NT);
+   {
+      constexpr int DD = C::DD, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D;
+      const double *Es = A + C::NF*C::ND;
+      // stage alpha: x pencils
+      constexpr int nGa = C::NF*DD, nLa = LL;
+      for (int it = tid; it < nGa + nLa; it += NT)
+      {
+         if (it < nGa)
+         {
+            double in[D1D], bo[Q1D], go[Q1D];
+#pragma unroll
+            for (int d = 0; d < D1D; d++) { in[d] = A[d + D1D*it]; }
+            pencil_fwd<D1D,Q1D>(tab.B, in, bo);
+            pencil_fwd<D1D,Q1D>(tab.G, in, go);
+#pragma unroll
+            for (int q = 0; q < Q1D; q++) { Bx[q + Q1D*it] = bo[q]; Gx[q + Q1D*it] = go[q]; }
+         }
+         else
+         {
+            const int r = it - nGa;                   // ly + L1D*lz
+            double in[L1D], out[Q1D];
+#pragma unroll
+            for (int l = 0; l < L1D; l++) { in[l] = Es[l + L1D*r]; }
+            pencil_fwd<L1D,Q1D>(tab.BL, in, out);
+#pragma unroll
+            for (int q = 0; q < Q1D; q++) { E1[q + Q1D*r] = out[q]; }   // [lz][ly][qx]
+         }
+      }
+      __syncthreads();
+      // stage beta: y pencils (BB | GB | BG overwrite the dofs, which are dead now)
+      constexpr int nGb = C::NF*D1D*Q1D, nLb = L1D*Q1D;
+      for (int it = tid; it < nGb + nLb; it += NT)
+      {
+         if (it < nGb)
+         {
+            const int qx = it % Q1D, fz = it / Q1D;   // fz = dz + D1D*f
+            double xb[D1D], xg[D1D], bb[Q1D], gb[Q1D], bg[Q1D];
+#pragma unroll
+            for (int d = 0; d < D1D; d++)
+            {
+               xb[d] = Bx[qx + Q1D*(d + D1D*fz)];
+               xg[d] = Gx[qx + Q1D*(d + D1D*fz)];
+            }
+            pencil_fwd<D1D,Q1D>(tab.B, xb, bb);
+            pencil_fwd<D1D,Q1D>(tab.B, xg, gb);
+            pencil_fwd<D1D,Q1D>(tab.G, xb, bg);
+#pragma unroll
+            for (int q = 0; q < Q1D; q++)
+            {
+               const int o = qx + Q1D*q + QQ*fz;      // [f][dz][qy][qx]
+               BB[o] = bb[q]; GB[o] = gb[q]; BG[o] = bg[q];
+            }
+         }
+         else
+         {
+            const int r = it - nGb;
+            const int qx = r % Q1D, lz = r / Q1D;
+            double in[L1D], out[Q1D];
+#pragma unroll
+            for (int l = 0; l < L1D; l++) { in[l] = E1[qx + Q1D*(l + L1D*lz)]; }
+            pencil_fwd<L1D,Q1D>(tab.BL, in, out);
+#pragma unroll
+            for (int q = 0; q < Q1D; q++) { E2[qx + Q1D*(q + Q1D*lz)] = out[q]; }   // [lz][qy][qx]
+         }
+      }
+      __syncthreads();
+   }
    // z pass + point physics
    const double gam = gamma[e];
    double dt_min = prm.dt_in;
@@ -267,7 +335,10 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
       const double *j0 = Jac0inv + eq*9;
 #pragma unroll
       for (int k = 0; k < 9; k++) { J0[k] = __ldg(j0 + k); }
-      const double dtq = qpoint<3>(J, dV, Eq[q], __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q),
+      double e_q = 0.0;
+#pragma unroll
+      for (int lz = 0; lz < C::L1D; lz++) { e_q += TBL[qz + Q1D*lz]*E2[col + C::QQ*lz]; }
+      const double dtq = qpoint<3>(J, dV, e_q, __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q),
                                    __ldg(inv_qweights + q), prm, sJ);
       dt_min = fmin(dt_min, dtq);
 #pragma unroll
