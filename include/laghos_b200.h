@@ -174,6 +174,14 @@ int lagb_pcg_vmass_all(lagb_ctx *ctx, const double *d_rhs, double *d_dv,
 int lagb_cg_emass(lagb_ctx *ctx, const double *d_b, double *d_x,
                   double rel_tol, int max_iter, int *h_iters);
 
+/* LagrangianHydroOperator::InternalEnergy / KineticEnergy (laghos_solver.cpp:639-697):
+ * sum_q rho0 detJ0 w e(q)  and  1/2 sum_q rho0 detJ0 w |v(q)|^2, summed over the ranks
+ * (the reference's MPI_Allreduce, :663, :693).  Evaluated as 1^t (M_L2 e) and 1/2 v^t (M_H1 v)
+ * with the PA mass kernels (partition of unity of the Bernstein basis; the mass coefficient equals
+ * rho0DetJ0w for the element-wise constant densities of the reference's problems).  Synchronous. */
+int lagb_internal_energy(lagb_ctx *ctx, const double *d_e, double *h_out);
+int lagb_kinetic_energy(lagb_ctx *ctx, const double *d_v, double *h_out);
+
 /* 2D Taylor-Green energy source (laghos_solver.cpp:455-465): d_esrc[ndofs_l2] */
 int lagb_taylor_source(lagb_ctx *ctx, const double *d_x, double *d_esrc);
 

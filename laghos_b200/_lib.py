@@ -53,7 +53,8 @@ class RunResult(C.Structure):
                 ("kernel_launches", C.c_int64), ("n_hist", C.c_int),
                 ("ndofs_h1_global", C.c_int64), ("ndofs_l2_global", C.c_int64), ("ne_global", C.c_int64),
                 ("mass_kernel_seconds", C.c_double), ("mass_kernel_launches", C.c_int64),
-                ("mass_kernel_ncomp", C.c_int64), ("work_mdof", C.c_double)]
+                ("mass_kernel_ncomp", C.c_int64), ("work_mdof", C.c_double),
+                ("energy_init", C.c_double), ("energy_final", C.c_double)]
 
 
 # every symbol include/laghos_b200.h declares (tests/test_abi_symbols.py checks the
@@ -69,7 +70,7 @@ lagb_qdata_ptr lagb_qdata_h0 lagb_qdata_set_h0 lagb_dev_malloc lagb_dev_free lag
 lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_memcpy_h2d_bg lagb_memcpy_d2h_bg lagb_wait_copies lagb_host_alloc_pinned lagb_host_free_pinned lagb_vec_fill
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
-lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set""".split()
+lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set lagb_internal_energy lagb_kinetic_energy""".split()
 
 
 def load_library():
@@ -124,6 +125,8 @@ def load_library():
     lib.lagb_pcg_vmass_all.argtypes = [vp, vp, vp, dbl, i32, c_int_p]
     lib.lagb_cg_emass.argtypes = [vp, vp, vp, dbl, i32, c_int_p]
     lib.lagb_taylor_source.argtypes = [vp, vp, vp]
+    lib.lagb_internal_energy.argtypes = [vp, vp, c_double_p]
+    lib.lagb_kinetic_energy.argtypes = [vp, vp, c_double_p]
     lib.lagb_qdata_ptr.argtypes = [vp, i32]
     lib.lagb_qdata_ptr.restype = vp
     lib.lagb_qdata_h0.argtypes = [vp]

@@ -229,6 +229,16 @@ class Context:
         _check(self.lib, self.lib.lagb_cg_emass(self.h, self._p(b), self._p(x), rel_tol, max_iter, C.byref(it)))
         return x, it.value
 
+    def internal_energy(self, e):
+        out = C.c_double()
+        _check(self.lib, self.lib.lagb_internal_energy(self.h, self._p(e), C.byref(out)))
+        return out.value
+
+    def kinetic_energy(self, v):
+        out = C.c_double()
+        _check(self.lib, self.lib.lagb_kinetic_energy(self.h, self._p(v), C.byref(out)))
+        return out.value
+
     def taylor_source(self, x):
         e = self.empty(self.P.ndofs_l2)
         _check(self.lib, self.lib.lagb_taylor_source(self.h, self._p(x), self._p(e)))
@@ -314,6 +324,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
                quad_tstep=r.timing.quad_tstep, wall_seconds=r.wall_seconds, device_seconds=r.device_seconds,
                mass_kernel_seconds=r.mass_kernel_seconds, mass_kernel_launches=r.mass_kernel_launches,
                mass_kernel_ncomp=r.mass_kernel_ncomp, work_mdof=r.work_mdof,
+               energy_init=r.energy_init, energy_final=r.energy_final,
                h2d_bytes_per_step=r.h2d_bytes_per_step, d2h_bytes_per_step=r.d2h_bytes_per_step,
                kernel_launches=r.kernel_launches, ndofs_h1_global=r.ndofs_h1_global,
                ndofs_l2_global=r.ndofs_l2_global, ne_global=r.ne_global,

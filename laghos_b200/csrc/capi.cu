@@ -663,6 +663,48 @@ int lagb_cg_emass(lagb_ctx *h, const double *d_b, double *d_x, double rel_tol, i
    return LAGB_OK;
 }
 
+// sum over ranks of dot(a, b) (n entries); scratch: d_part, d_tmp + 8
+static int global_dot(Ctx &c, const double *a, const double *b, int64_t n, double *out)
+{
+   const int g = vec_grid(n);
+   pcg::dot_partial<1><<<g, pcg::RB, 0, c.stream>>>(n, 0, a, b, nullptr, c.d_part);
+   LAGB_LAUNCH_CHECK();
+   pcg::reduce_partials<1><<<1, pcg::RB, 0, c.stream>>>(g, c.d_part, c.d_tmp + 8);
+   LAGB_LAUNCH_CHECK();
+   int rc = allreduce_sum(c, c.d_tmp + 8, 1); if (rc) { return rc; }
+   LAGB_CUDA(cudaMemcpyAsync(c.h_scal + 8, c.d_tmp + 8, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+   LAGB_CUDA(cudaStreamSynchronize(c.stream));
+   *out = c.h_scal[8];
+   return LAGB_OK;
+}
+
+int lagb_internal_energy(lagb_ctx *h, const double *d_e, double *h_out)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("internal_energy: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   int rc = ks.mass_l2(c, d_e, c.d_lz); if (rc) { return rc; }                  // M_L2 e (element local)
+   pcg::vec_fill<<<vec_grid(c.ndofs_l2), pcg::RB, 0, c.stream>>>(c.d_lr, 1.0, c.ndofs_l2);
+   LAGB_LAUNCH_CHECK();
+   return global_dot(c, c.d_lr, c.d_lz, c.ndofs_l2, h_out);
+}
+
+int lagb_kinetic_energy(lagb_ctx *h, const double *d_v, double *h_out)
+{
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("kinetic_energy: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   const int64_t n = c.ndofs*c.dim;
+   LAGB_CUDA(cudaMemsetAsync(c.d_z, 0, sizeof(double)*n, c.stream));
+   // rank-local element contributions only (no shared-dof sum): v^t (M_loc v) summed over ranks
+   // counts every element once
+   int rc = ks.mass_h1(c, c.dim, d_v, c.d_z, false); if (rc) { return rc; }
+   double s = 0.0;
+   rc = global_dot(c, d_v, c.d_z, n, &s); if (rc) { return rc; }
+   *h_out = 0.5*s;
+   return LAGB_OK;
+}
+
 int lagb_taylor_source(lagb_ctx *h, const double *d_x, double *d_esrc)
 {
    Ctx &c = h->c;

@@ -373,6 +373,8 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          default: fprintf(stderr, "Unknown ODE solver type: %d\n", opt->ode_solver_type); lagb_ctx_destroy(ctx); return 3;
       }
       ode_solver->Init(hydro);
+      Vector v_gf0, e_gf0; v_gf0.MakeRef(S, NV, NV); e_gf0.MakeRef(S, 2*NV, P.ndofs_l2);
+      res->energy_init = hydro.InternalEnergy(e_gf0) + hydro.KineticEnergy(v_gf0);   // laghos.cpp:664-665
       hydro.ResetTimeStepEstimate();
       double t = 0.0, dt = hydro.GetTimeStepEstimate(S), t_old;
       bool last_step = false;
@@ -484,6 +486,8 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          res->fom[4] = T4;
          res->work_mdof = 1e-6*(H1GTVSize*H1iter + timed_steps*(H1GTVSize + L2GTVSize) + sizes[3]*P.NQ);
       }
+      res->energy_final = hydro.InternalEnergy(e_gf0) + hydro.KineticEnergy(v_gf0);      // laghos.cpp:956-962
+      if (opt->verbose && opt->rank == 0) { printf("\nEnergy  diff: %.2e\n", std::fabs(res->energy_init - res->energy_final)); }
       if (S_out) { std::vector<double> tmp; S.HostRead(tmp); memcpy(S_out, tmp.data(), sizeof(double)*N); }
       if (opt->verbose && opt->rank == 0)
       {

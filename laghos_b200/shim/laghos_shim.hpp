@@ -193,6 +193,9 @@ public:
    double GetTimeStepEstimate(const Vector &S) const;
    void ResetTimeStepEstimate() const;
    void ResetQuadratureData() const { qdata_is_current = false; }
+   // reference laghos_solver.cpp:639-697 (the MPI_Allreduce is inside the C-ABI call)
+   double InternalEnergy(const Vector &e) const { double v; LAGHOS_CHECK(lagb_internal_energy(ctx, e.Read(), &v)); return v; }
+   double KineticEnergy(const Vector &v_) const { double v; LAGHOS_CHECK(lagb_kinetic_energy(ctx, v_.Read(), &v)); return v; }
    void StatePending() const { state_pending = true; }
    void WaitState() const { if (state_pending) { LAGHOS_CHECK(lagb_wait_copies(ctx)); state_pending = false; } }
    void UpdateQuadratureData(const Vector &S) const;
@@ -273,6 +276,7 @@ typedef struct lagb_run_result
    int64_t mass_kernel_launches;
    int64_t mass_kernel_ncomp;       // components per launch (3 = batched PCG)
    double work_mdof;                // numerator of the FOM: 1e-6 * (H1 dofs x CG its + (H1+L2) dofs x stages + quad points x updates)
+   double energy_init, energy_final; // IE + KE before / after the run (laghos.cpp:664-665, 956-962 "Energy diff")
 } lagb_run_result;
 
 // hist: [2*hist_cap] (ti, |e|) pairs after every accepted step; S_out (optional): final state on the host

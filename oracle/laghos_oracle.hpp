@@ -161,6 +161,43 @@ struct Kernels
          for (int i = 0; i < ND; i++) { diag[map[i]] += Y[i]; }
       }
    }
+   // reference InternalEnergy / KineticEnergy (laghos_solver.cpp:639-697) through
+   // ComputeVolumeIntegral (:565-637): sum_q rho0DetJ0w(q) * sum_k f_k(q)^norm, f = e (norm 1)
+   // or v (norm 2), interpolated at the quadrature points
+   static double EnergyIntegralL2(const Problem &P, const double *rho0DetJ0w, const double *e_gf)
+   {
+      const double *BL = P.tab.BL.data();
+      double sum = 0.0;
+      for (int e = 0; e < P.NE; e++)
+      {
+         double QQ[NQ];
+         interp<L1D>(BL, e_gf + (size_t)e*NL, QQ);
+         const double *d = rho0DetJ0w + (size_t)e*NQ;
+         for (int q = 0; q < NQ; q++) { sum += QQ[q]*d[q]; }
+      }
+      return sum;
+   }
+   static double EnergyIntegralH1(const Problem &P, const double *rho0DetJ0w, const double *v)
+   {
+      const double *B = P.tab.B.data();
+      double sum = 0.0;
+      for (int e = 0; e < P.NE; e++)
+      {
+         const int *map = P.h1_map.data() + (size_t)e*ND;
+         const double *d = rho0DetJ0w + (size_t)e*NQ;
+         double vmag[NQ];
+         for (int q = 0; q < NQ; q++) { vmag[q] = 0.0; }
+         for (int c = 0; c < DIM; c++)
+         {
+            double X[ND], QQ[NQ];
+            for (int i = 0; i < ND; i++) { X[i] = v[(size_t)c*P.ndofs_h1 + map[i]]; }
+            interp<D1D>(B, X, QQ);
+            for (int q = 0; q < NQ; q++) { vmag[q] += QQ[q]*QQ[q]; }
+         }
+         for (int q = 0; q < NQ; q++) { sum += vmag[q]*d[q]; }
+      }
+      return sum;
+   }
    // L2 (Bernstein) mass, block diagonal: y = BL^t D BL x
    static void MassL2(const Problem &P, const double *D, const double *x, double *y, int e0, int e1)
    {
@@ -440,6 +477,8 @@ struct KernelTable
    void (*MassH1)(const Problem&, const double*, const double*, double*, int, int) = nullptr;
    void (*MassH1Diag)(const Problem&, const double*, double*) = nullptr;
    void (*MassL2)(const Problem&, const double*, const double*, double*, int, int) = nullptr;
+   double (*EnergyIntegralL2)(const Problem&, const double*, const double*) = nullptr;
+   double (*EnergyIntegralH1)(const Problem&, const double*, const double*) = nullptr;
    void (*ForceMult)(const Problem&, const double*, const double*, double*, int, int) = nullptr;
    void (*ForceMultTranspose)(const Problem&, const double*, const double*, double*, int, int) = nullptr;
    void (*Rho0DetJ0Vol)(const Problem&, const double*, const double*, QuadratureData&, std::vector<double>&, double&) = nullptr;
@@ -453,6 +492,7 @@ static KernelTable make_table()
    using K = Kernels<DIM, D1D, Q1D>;
    KernelTable t;
    t.MassH1 = &K::MassH1; t.MassH1Diag = &K::MassH1Diag; t.MassL2 = &K::MassL2;
+   t.EnergyIntegralL2 = &K::EnergyIntegralL2; t.EnergyIntegralH1 = &K::EnergyIntegralH1;
    t.ForceMult = &K::ForceMult; t.ForceMultTranspose = &K::ForceMultTranspose;
    t.Rho0DetJ0Vol = &K::Rho0DetJ0Vol; t.QUpdate = &K::QUpdate; t.TaylorSource = &K::TaylorSource;
    return t;
@@ -633,6 +673,9 @@ struct Hydro
       for_elements_scatter([&](int a, int b) { K.MassH1(P, massD.data(), x, y, a, b); });
       if (ess) { for (int i : *ess) { y[i] = 0.0; } }
    }
+   // reference LagrangianHydroOperator::InternalEnergy / KineticEnergy (laghos_solver.cpp:639-697)
+   double InternalEnergy(const double *e_gf) const { return K.EnergyIntegralL2(P, qd.rho0DetJ0w.data(), e_gf); }
+   double KineticEnergy(const double *v) const { return 0.5*K.EnergyIntegralH1(P, qd.rho0DetJ0w.data(), v); }
    void EMassMult(const double *x, double *y) const
    {
       for_elements([&](int a, int b) { K.MassL2(P, massD.data(), x, y, a, b); });
@@ -866,6 +909,7 @@ struct RunResult
    double fom[5] = {0, 0, 0, 0, 0};
    TimingData timer;
    int stages = 4;
+   double energy_init = 0, energy_final = 0;   // IE + KE (laghos.cpp:664-665, 956-962)
 };
 
 // time loop: reference laghos.cpp:706-778 + ODE solvers (MFEM RK4Solver et al.,
@@ -876,6 +920,7 @@ static inline RunResult run(const Problem &P, const RunOptions &opt, std::vector
    const int64_t N = P.s_size(), NV = P.h1_vsize();
    std::vector<double> S(P.S0), S_old(N), k(N), y(N), z(N), V(NV), S0(N);
    RunResult res;
+   res.energy_init = hydro.InternalEnergy(S.data() + 2*NV) + hydro.KineticEnergy(S.data() + NV);
    hydro.ResetTimeStepEstimate();
    double t = 0.0, dt = hydro.GetTimeStepEstimate(S.data()), t_old;
    bool last_step = false;
@@ -977,6 +1022,7 @@ static inline RunResult run(const Problem &P, const RunOptions &opt, std::vector
       }
    }
    res.steps = steps; res.t = t; res.dt = dt;
+   res.energy_final = hydro.InternalEnergy(S.data() + 2*NV) + hydro.KineticEnergy(S.data() + NV);
    int stages = 1;
    switch (opt.ode_solver_type) { case 2: stages = 2; break; case 3: stages = 3; break; case 4: stages = 4; break; case 7: stages = 2; break; }
    res.stages = stages;

@@ -117,6 +117,8 @@ void orc_taylor_source(void *hh, const double *x, double *esrc)
    OrcHandle *h = (OrcHandle*)hh;
    h->H->K.TaylorSource(h->P, x, esrc);
 }
+double orc_internal_energy(void *hh, const double *e) { return ((OrcHandle*)hh)->H->InternalEnergy(e); }
+double orc_kinetic_energy(void *hh, const double *v) { return ((OrcHandle*)hh)->H->KineticEnergy(v); }
 // dS_dt = f(S): one call of LagrangianHydroOperator::Mult with fresh quadrature data
 void orc_mult(void *hh, const double *S, double *dS_dt)
 {
@@ -148,7 +150,7 @@ int orc_run(const char *mesh, int rs, int problem, int ok, int ot, int oq, doubl
       for (int i = 0; i < 5; i++) { out[5 + i] = r.fom[i]; }
       out[10] = r.timer.sw_cgH1; out[11] = r.timer.sw_cgL2; out[12] = r.timer.sw_force; out[13] = r.timer.sw_qdata;
       out[14] = (double)r.timer.H1iter; out[15] = (double)r.timer.L2iter; out[16] = (double)r.timer.quad_tstep;
-      out[17] = r.stages;
+      out[17] = r.stages; out[19] = r.energy_init; out[20] = r.energy_final;
       int n = 0;
       for (auto &h : r.e_norm_history) { if (n < hist_cap) { hist[2*n] = h.first; hist[2*n + 1] = h.second; n++; } }
       out[18] = n;

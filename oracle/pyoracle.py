@@ -43,6 +43,10 @@ def load():
         lib.orc_cg_emass.argtypes = [C.c_void_p, dp, dp]
         lib.orc_taylor_source.argtypes = [C.c_void_p, dp, dp]
         lib.orc_mult.argtypes = [C.c_void_p, dp, dp]
+        lib.orc_internal_energy.argtypes = [C.c_void_p, dp]
+        lib.orc_internal_energy.restype = C.c_double
+        lib.orc_kinetic_energy.argtypes = [C.c_void_p, dp]
+        lib.orc_kinetic_energy.restype = C.c_double
         lib.orc_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                 C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                 dp, dp, C.c_int, dp]
@@ -146,6 +150,12 @@ class Oracle:
         self.lib.orc_taylor_source(self.h, _p(x), _p(e))
         return e
 
+    def internal_energy(self, e):
+        return self.lib.orc_internal_energy(self.h, _p(np.ascontiguousarray(e)))
+
+    def kinetic_energy(self, v):
+        return self.lib.orc_kinetic_energy(self.h, _p(np.ascontiguousarray(v)))
+
     def mult(self, S):
         d = np.zeros(self.s_size)
         self.lib.orc_mult(self.h, _p(S), _p(d))
@@ -173,6 +183,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     res = dict(steps=int(out[0]), ti_last=int(out[1]), t=out[2], dt=out[3], e_norm=out[4], fom=list(out[5:10]),
                t_cgH1=out[10], t_cgL2=out[11], t_force=out[12], t_qdata=out[13], H1iter=int(out[14]),
                L2iter=int(out[15]), quad_tstep=int(out[16]), stages=int(out[17]),
+               energy_init=out[19], energy_final=out[20],
                hist=[(int(hist[2 * i]), float(hist[2 * i + 1])) for i in range(n)])
     if want_state:
         res["S"] = S

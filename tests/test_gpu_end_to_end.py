@@ -62,6 +62,9 @@ def test_vs_oracle_e_norm(built, cfg, batched):
         assert ti_g == ti_o
         assert abs(e_g - e_o) <= tol * abs(e_o), (ti_g, e_g, e_o)
     assert abs(rg["dt"] - ro["dt"]) <= tol * ro["dt"]
+    # total energy IE + KE before / after (the reference's "Energy diff" line, laghos.cpp:956-962)
+    assert abs(rg["energy_init"] - ro["energy_init"]) <= 1e-12 * abs(ro["energy_init"])
+    assert abs(rg["energy_final"] - ro["energy_final"]) <= max(tol, 1e-9) * abs(ro["energy_final"])
 
 
 def test_readme_run2_gpu(built):

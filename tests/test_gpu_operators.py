@@ -172,3 +172,15 @@ def test_taylor_source_2d(pair):
     ref = O.taylor_source(S[:P.h1_vsize].copy())
     for c in ctxs:
         assert relerr(c.taylor_source(c.dev(S[:P.h1_vsize])).cpu().numpy(), ref) < 1e-12
+
+
+def test_energies(pair):
+    """InternalEnergy / KineticEnergy (reference laghos_solver.cpp:639-697) vs the oracle's quadrature sums."""
+    P, O, ctxs = pair
+    rng = np.random.default_rng(14)
+    e = rng.uniform(0.5, 1.5, P.ndofs_l2)
+    v = rng.uniform(-1, 1, P.h1_vsize)
+    ie_ref, ke_ref = O.internal_energy(e), O.kinetic_energy(v)
+    for c in ctxs:
+        assert abs(c.internal_energy(c.dev(e)) - ie_ref) <= 1e-12 * abs(ie_ref)
+        assert abs(c.kinetic_energy(c.dev(v)) - ke_ref) <= 1e-12 * abs(ke_ref)

@@ -108,3 +108,19 @@ def test_partition_single_phase_sum(built, pgrid):
             else:
                 owner_val[g] = out[r][i]
     assert sum(int(p.owner_mask.sum()) for p in parts) == G.ndofs_h1
+
+
+def test_oracle_energies(built):
+    """InternalEnergy / KineticEnergy (reference laghos_solver.cpp:639-697): the Sedov blast energy is
+    E0/2^dim, and the integrals equal 1^t M_L2 e and 1/2 v^t M_H1 v (the form the CUDA path evaluates)."""
+    import pyoracle
+    O = pyoracle.Oracle("cube01_hex", 1, 1, 2, 1)
+    e = O.S0[2 * O.h1_vsize:]
+    assert abs(O.internal_energy(e) - 0.125) < 1e-15
+    assert abs(O.internal_energy(e) - O.emass_mult(e).sum()) < 1e-15
+    v = np.random.default_rng(0).uniform(-1, 1, O.h1_vsize)
+    n = O.ndofs_h1
+    ke = 0.5 * sum(float(v[c * n:(c + 1) * n] @ O.vmass_mult(np.ascontiguousarray(v[c * n:(c + 1) * n]))) for c in range(3))
+    assert abs(O.kinetic_energy(v) - ke) < 1e-14 * ke
+    r = pyoracle.run(mesh="cube01_hex", rs=1, problem=0, ok=2, ot=1, max_tsteps=10, t_final=1e9, cg_tol=1e-12)
+    assert abs(r["energy_init"] - r["energy_final"]) < 1e-9 * r["energy_init"]   # smooth Taylor-Green: RK4 conserves to ~1e-11
