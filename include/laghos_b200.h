@@ -66,6 +66,13 @@ int lagb_problem_create_rect(lagb_problem **out, int dim,
                              const double *bx, int nbx, const double *by, int nby,
                              const double *bz, int nbz, int rs, int problem,
                              int ok, int ot, int oq, double blast_scale, int impose_visc);
+/* the same from a mesh FILE in the reference's format (MFEM mesh v1.0, reference data/<name>.mesh;
+ * `-m <file>`, laghos.cpp:380-393): rectilinear quad / hex meshes with the reference's boundary
+ * attribute convention (attribute k = faces of constant x_{k-1}); anything else is rejected. */
+int lagb_problem_create_file(lagb_problem **out, const char *path, int rs, int problem,
+                             int ok, int ot, int oq, double blast_scale, int impose_visc);
+/* per-axis breakpoints of the (refined, global) mesh */
+int lagb_problem_mesh_breaks(const lagb_problem *p, int axis, const double **brk, int32_t *n);
 /* one rank's part of an element-partitioned run: the element box of
  * `rank` in the process grid pgrid[3]; boundary conditions and the Sedov delta refer
  * to the global mesh.  Replaces ParMesh(MPI_COMM_WORLD, mesh, partitioning)

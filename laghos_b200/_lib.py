@@ -60,6 +60,7 @@ class RunResult(C.Structure):
 # every symbol include/laghos_b200.h declares (tests/test_abi_symbols.py checks the
 # header against this list and against the built library)
 SYMBOLS = """lagb_last_error lagb_kernel_launch_count lagb_problem_create lagb_problem_create_rect
+lagb_problem_create_file lagb_problem_mesh_breaks
 lagb_problem_create_part lagb_problem_nnbr lagb_problem_nbr lagb_problem_owner_mask
 lagb_problem_destroy lagb_problem_get_info lagb_problem_h1_map lagb_problem_ess lagb_problem_S0
 lagb_problem_rho0_gf lagb_problem_rho0_q lagb_problem_gamma lagb_problem_qweights lagb_problem_table
@@ -89,6 +90,8 @@ def load_library():
     lib.lagb_problem_create.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i32, i32, dbl, i32]
     lib.lagb_problem_create_rect.argtypes = [C.POINTER(vp), i32, c_double_p, i32, c_double_p, i32, c_double_p, i32,
                                              i32, i32, i32, i32, i32, dbl, i32]
+    lib.lagb_problem_create_file.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i32, i32, dbl, i32]
+    lib.lagb_problem_mesh_breaks.argtypes = [vp, i32, C.POINTER(c_double_p), c_int_p]
     lib.lagb_problem_create_part.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32, i32, i32, i32, dbl, i32, i32,
                                              C.POINTER(i32 * 3)]
     lib.lagb_problem_nnbr.argtypes = [vp]

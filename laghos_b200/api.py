@@ -26,16 +26,21 @@ class Problem:
     """Host-side setup (mesh, tables, initial conditions): reference laghos.cpp:380-656."""
 
     def __init__(self, mesh="cube01_hex", rs=0, problem=1, ok=2, ot=1, oq=-1, blast_scale=None, impose_visc=False,
-                 rank=0, pgrid=None):
+                 rank=0, pgrid=None, mesh_file=None, dim=None):
         self.lib = load_library()
-        dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
+        if dim is None:
+            dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
         if blast_scale is None:
             blast_scale = 1.0 / 2 ** dim  # E0 = 1 (laghos.cpp:166, 603-604)
         self.args = dict(mesh=mesh, rs=rs, problem=problem, ok=ok, ot=ot, oq=oq, blast_scale=blast_scale,
                          impose_visc=impose_visc)
         h = C.c_void_p()
         self.pgrid = pgrid
-        if pgrid is None:
+        if mesh_file is not None:
+            # reference `-m <file>`: MFEM mesh v1.0, rectilinear (pass dim for the default blast scale)
+            _check(self.lib, self.lib.lagb_problem_create_file(C.byref(h), str(mesh_file).encode(), rs, problem, ok, ot,
+                                                               oq, blast_scale, int(impose_visc)))
+        elif pgrid is None:
             _check(self.lib, self.lib.lagb_problem_create(C.byref(h), mesh.encode(), rs, problem, ok, ot, oq,
                                                           blast_scale, int(impose_visc)))
         else:
@@ -95,6 +100,12 @@ class Problem:
         if not ptr:
             return np.ones(self.ndofs_h1, dtype=np.uint8)
         return self._arr(ptr, self.ndofs_h1, np.uint8)
+
+    def mesh_breaks(self, axis):
+        ptr = c_double_p()
+        n = C.c_int32()
+        _check(self.lib, self.lib.lagb_problem_mesh_breaks(self.h, axis, C.byref(ptr), C.byref(n)))
+        return self._arr(ptr, n.value, np.float64)
 
     def table(self, which, n):
         return self._arr(self.lib.lagb_problem_table(self.h, which), n, np.float64)

@@ -2,6 +2,7 @@
 #include "../../include/laghos_b200.h"
 #include "host/problem.hpp"
 #include "host/partition.hpp"
+#include "host/mesh_reader.hpp"
 #include <string>
 
 namespace lagb { void set_error(const std::string &msg); }
@@ -45,6 +46,25 @@ int lagb_problem_create(lagb_problem **out, const char *mesh_name, int rs, int p
                                    coarse[1].data(), (int)coarse[1].size(),
                                    coarse[2].data(), (int)coarse[2].size(), rs, problem, ok, ot, oq,
                                    blast_scale, impose_visc);
+}
+
+int lagb_problem_create_file(lagb_problem **out, const char *path, int rs, int problem,
+                             int ok, int ot, int oq, double blast_scale, int impose_visc)
+{
+   std::vector<double> coarse[3]; int dim = 0; std::string err;
+   if (!path || !lagb::read_mfem_mesh_rectilinear(path, dim, coarse, err))
+   { lagb::set_error(std::string("mesh file: ") + (path ? err : "(null path)")); return LAGB_ERR_INVALID; }
+   return lagb_problem_create_rect(out, dim, coarse[0].data(), (int)coarse[0].size(),
+                                   coarse[1].data(), (int)coarse[1].size(),
+                                   coarse[2].data(), (int)coarse[2].size(), rs, problem, ok, ot, oq,
+                                   blast_scale, impose_visc);
+}
+
+int lagb_problem_mesh_breaks(const lagb_problem *p, int axis, const double **brk, int32_t *n)
+{
+   if (!p || axis < 0 || axis > 2) { return LAGB_ERR_INVALID; }
+   *brk = p->P.mesh.brk[axis].data(); *n = (int32_t)p->P.mesh.brk[axis].size();
+   return LAGB_OK;
 }
 
 int lagb_problem_create_part(lagb_problem **out, const char *mesh_name, int rs, int problem,
