@@ -2,6 +2,7 @@
 #include "ctx.hpp"
 #include <algorithm>
 #include "device/mass3d.cuh"
+#include "device/mass3d_shfl.cuh"
 #include "device/staged3d.cuh"
 
 namespace lagb {
@@ -37,6 +38,19 @@ struct TunedLaunch3D
       if (WITH_DEN) { c.dt_nblocks = grid; }
       return LAGB_OK;
    }
+   // experimental shuffle hand-off variant (device/mass3d_shfl.cuh), D1D = 4 only
+   template<int NC, bool WITH_DEN, int NB, int MINB>
+   static int mass_launch_shfl(Ctx &c, const double *x, double *y)
+   {
+      static_assert((NB*4) % 32 == 0, "a component group must be whole warps");
+      auto kern = tuned::mass3d_shfl<Q1D,NB,NC,WITH_DEN,MINB>;
+      const int grid = (c.NE + NB - 1)/NB;
+      if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d_shfl: partial buffer too small"); return LAGB_ERR_STATE; }
+      kern<<<grid, NC*NB*4, 0, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part);
+      LAGB_LAUNCH_CHECK();
+      if (WITH_DEN) { c.dt_nblocks = grid; }
+      return LAGB_OK;
+   }
    template<int NC, bool WITH_DEN>
    static int mass_launch(Ctx &c, const double *x, double *y)
    {
@@ -48,6 +62,8 @@ struct TunedLaunch3D
             case 2: return mass_launch_v<NC,WITH_DEN,16,3,true,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
+            case 5: if constexpr ((Q1D*Q1D) % 4 == 0) { return mass_launch_shfl<NC,WITH_DEN,8,4>(c, x, y); } break;
+            case 6: if constexpr ((Q1D*Q1D) % 4 == 0) { return mass_launch_shfl<NC,WITH_DEN,8,3>(c, x, y); } break;
          }
          return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants*.txt): 351 us
       }

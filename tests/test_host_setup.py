@@ -124,3 +124,29 @@ def test_oracle_energies(built):
     assert abs(O.kinetic_energy(v) - ke) < 1e-14 * ke
     r = pyoracle.run(mesh="cube01_hex", rs=1, problem=0, ok=2, ot=1, max_tsteps=10, t_final=1e9, cg_tol=1e-12)
     assert abs(r["energy_init"] - r["energy_final"]) < 1e-9 * r["energy_init"]   # smooth Taylor-Green: RK4 conserves to ~1e-11
+
+
+def test_quad_transpose_emulation():
+    """Index logic of the experimental shuffle hand-off (device/mass3d_shfl.cuh, quad_transpose): a two-step
+    xor butterfly over 4 lanes with compile-time register indices transposes the 4 x 4 block matrix
+    (lane j, slot m) <- (lane m, column 4k + j) and is an involution.  Emulated lane by lane."""
+    NK = 9
+    V = np.array([[100.0 * j + col for col in range(4 * NK)] for j in range(4)])
+
+    def transpose(V):
+        V = V.copy()
+        for p in (0, 2):
+            for k in range(NK):
+                send = [V[j, 4 * k + p] if (j & 1) else V[j, 4 * k + p + 1] for j in range(4)]
+                for j in range(4):
+                    V[j, 4 * k + p + (0 if j & 1 else 1)] = send[j ^ 1]
+        for s in (0, 1):
+            for k in range(NK):
+                send = [V[j, 4 * k + s] if (j & 2) else V[j, 4 * k + 2 + s] for j in range(4)]
+                for j in range(4):
+                    V[j, 4 * k + (s if j & 2 else 2 + s)] = send[j ^ 2]
+        return V
+
+    T = transpose(V)
+    assert all(T[j, 4 * k + m] == 100.0 * m + 4 * k + j for j in range(4) for k in range(NK) for m in range(4))
+    assert np.array_equal(transpose(T), V)
