@@ -1,4 +1,7 @@
-// EXPERIMENTAL, UNMEASURED (round-2 candidate; selected only with lagb_tune_set(ctx, 0, 5)).
+// EXPERIMENTAL (selected only with lagb_tune_set(ctx, 0, 5)).  Measured on B200, cube01_hex -rs 5 Q3Q2, NC = 3:
+// correct (checksum identical to the production kernel) but SLOWER: 488 us vs 339 us.  The whole plane lives in
+// registers (168 per thread -> 4 CTAs = 12 warps per SM, against 18 warps at 96 registers) and the
+// butterflies add 72 selects + 72 SHFL per transpose; the shared-memory planes stay the production path.
 //
 // mass3d with a register/shuffle hand-off between the slice phases (A, C) and the column phase (B)
 // instead of shared-memory planes.  Motivation (profiles/ncu_mass3d_r1_final.txt): the LSU data pipe
