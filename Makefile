@@ -25,9 +25,6 @@ build/laghos_shim.o: laghos_b200/shim/laghos_shim.cpp laghos_b200/shim/laghos_sh
 laghos_b200/lib/liblaghos_b200.so: $(OBJ)
 	@mkdir -p laghos_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -ldl
-build/laghos: laghos_b200/shim/laghos_main.cpp laghos_b200/lib/liblaghos_b200.so
-	$(CXX) $(CXXFLAGS) -o $@ $< -Llaghos_b200/lib -llaghos_b200 -Wl,-rpath,'$$ORIGIN/../laghos_b200/lib'
-
 oracle/_build/liboracle.so: oracle/oracle_capi.cpp oracle/laghos_oracle.hpp oracle/smallmat.hpp $(HOST_HDRS)
 	@mkdir -p oracle/_build
 	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -o $@ oracle/oracle_capi.cpp -lpthread

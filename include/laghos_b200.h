@@ -118,6 +118,9 @@ typedef struct lagb_ctx_desc
    int32_t use_visc, use_vort;
    int32_t device;                   /* CUDA device ordinal */
    int32_t kernel_variant;           /* 0 = tuned kernels where available, 1 = generic one-thread-per-element kernels */
+   int32_t elem_grid[3];             /* optional hint: elements are numbered lexicographically (x fastest) on an
+                                        nx*ny*nz grid; {0,0,0} = unstructured.  Only the batching of the mass apply
+                                        (bricks vs consecutive elements) depends on it, never the result's value set */
 } lagb_ctx_desc;
 
 int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *desc, void *stream);
@@ -265,8 +268,19 @@ int lagb_stopwatch_start(lagb_ctx *ctx);
 int lagb_stopwatch_stop(lagb_ctx *ctx, double *seconds);   /* synchronises */
 int lagb_profile_mass(lagb_ctx *ctx, int enable);
 int lagb_profile_mass_get(lagb_ctx *ctx, double *seconds, int64_t *launches);
-/* kernel tuning knobs (tools/microbench.py): key 0 = launch variant of the 3-component mass apply */
+/* kernel tuning knobs (tools/microbench.py): key 0 = launch variant of the legacy 3-component mass apply,
+ * 1 = Force/Force^T, 2 = QUpdate, 3 = legacy 1-component mass, 4 = brick mass apply variant,
+ * 5 = 1: no programmatic dependent launch between the colours, 6 = 1: legacy (atomic) mass path */
 int lagb_tune_set(lagb_ctx *ctx, int key, int value);
+/* HOST only (no CUDA call): builds the coloured brick schedule of the mass apply for the gather map
+ * h_map [NE*ND] (grid = structured element grid hint or NULL, NB = elements per batch) and verifies
+ * the invariants the kernels rely on (every element once, colours conflict-free, exactly one first
+ * writer per dof, CSR consistent).  stats: nbatch, ncolors, ntables, max unique, padded unique,
+ * touched dofs, brick shape bx+100*by+10000*bz, total unique entries.  Replaces nothing in the
+ * reference: MFEM's ElementRestriction builds its offsets/indices arrays at the same point
+ * (laghos_assembly.cpp:133-134). */
+int lagb_host_batch_plan_check(const int32_t *h_map, int NE, int ND, int64_t ndofs, const int32_t grid[3],
+                               int NB, int64_t stats[8]);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ class CtxDesc(C.Structure):
                 ("h_B", C.c_void_p), ("h_G", C.c_void_p), ("h_BL", C.c_void_p),
                 ("h_qweights", C.c_void_p), ("h_gamma", C.c_void_p),
                 ("use_visc", C.c_int32), ("use_vort", C.c_int32), ("device", C.c_int32),
-                ("kernel_variant", C.c_int32)]
+                ("kernel_variant", C.c_int32), ("elem_grid", C.c_int32 * 3)]
 
 
 class Timing(C.Structure):
@@ -71,7 +71,8 @@ lagb_qdata_ptr lagb_qdata_h0 lagb_qdata_set_h0 lagb_dev_malloc lagb_dev_free lag
 lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_memcpy_h2d_bg lagb_memcpy_d2h_bg lagb_wait_copies lagb_host_alloc_pinned lagb_host_free_pinned lagb_vec_fill
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
-lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set lagb_internal_energy lagb_kinetic_energy""".split()
+lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set lagb_internal_energy lagb_kinetic_energy
+lagb_host_batch_plan_check""".split()
 
 
 def load_library():
@@ -117,6 +118,7 @@ def load_library():
     lib.lagb_vmass_diag.argtypes = [vp, vp]
     lib.lagb_vmass_mult_all.argtypes = [vp, vp, vp]
     lib.lagb_tune_set.argtypes = [vp, i32, i32]
+    lib.lagb_host_batch_plan_check.argtypes = [c_int_p, i32, i32, i64, c_int_p, i32, C.POINTER(i64)]
     lib.lagb_emass_mult.argtypes = [vp, vp, vp]
     lib.lagb_force_mult.argtypes = [vp, vp, vp]
     lib.lagb_force_mult_transpose.argtypes = [vp, vp, vp]

@@ -122,7 +122,7 @@ class Problem:
 class Context:
     """Device context: QuadratureData + operators (reference laghos_solver.hpp:97-205)."""
 
-    def __init__(self, problem, device=0, variant=0, setup=True):
+    def __init__(self, problem, device=0, variant=0, setup=True, grid_hint=True):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -145,6 +145,9 @@ class Context:
         d.h_qweights = C.cast(lib.lagb_problem_qweights(problem.h), C.c_void_p)
         d.h_gamma = C.cast(lib.lagb_problem_gamma(problem.h), C.c_void_p)
         d.use_visc, d.use_vort, d.device, d.kernel_variant = problem.use_visc, problem.use_vort, device, variant
+        if grid_hint:
+            for k in range(3):   # the problem's meshes are Cartesian with lexicographic element numbering
+                d.elem_grid[k] = (int(problem.info.n1[k]) - 1) // (problem.D1D - 1) if k < problem.dim else 1
         h = C.c_void_p()
         # the context runs on torch's current stream so that torch.cuda.Event timing sees it
         stream = torch.cuda.current_stream(self.device).cuda_stream

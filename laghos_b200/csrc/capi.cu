@@ -1,6 +1,7 @@
 // C ABI implementation (include/laghos_b200.h): context, operator entry points,
 // device-resident PCG driver, timers, NCCL plumbing.
 #include "ctx.hpp"
+#include "host/batch_plan.hpp"
 #include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
@@ -253,6 +254,37 @@ template<typename T> static int dev_upload(T **p, const T *h, size_t n)
    return LAGB_OK;
 }
 
+// Brick schedule of the H1 mass apply for NB elements per batch: built on the host from the gather
+// map on first use, uploaded once (host/batch_plan.hpp).
+int get_plan(Ctx &c, int NB, const DevPlan **out)
+{
+   auto it = c.plans.find(NB);
+   if (it != c.plans.end()) { *out = &it->second; return LAGB_OK; }
+   BatchPlan bp; std::string err;
+   const int shape[3] = {0, 0, 0};
+   if (bp.build(c.h_map.data(), c.NE, c.ND, c.ndofs, c.elem_grid, NB, shape, err)) { set_error(err); return LAGB_ERR_INVALID; }
+   DevPlan dp;
+   dp.NB = NB; dp.UP = bp.UP; dp.nbatch = bp.nbatch; dp.ncolors = bp.ncolors; dp.ntab = bp.ntab; dp.color_begin = bp.color_begin;
+   // lidx rows padded to a multiple of 8 entries (16-byte vector loads)
+   const int NDP = ((c.ND + 7)/8)*8;
+   std::vector<uint16_t> lp((size_t)bp.ntab*NB*NDP, 0);
+   for (int t = 0; t < bp.ntab; t++)
+      for (int e = 0; e < NB; e++)
+         for (int i = 0; i < c.ND; i++) { lp[((size_t)t*NB + e)*NDP + i] = bp.lidx[((size_t)t*NB + e)*c.ND + i]; }
+   int rc = 0;
+   rc |= dev_upload(&dp.belem, bp.elem.data(), bp.elem.size());
+   rc |= dev_upload(&dp.bnuniq, bp.nuniq.data(), bp.nuniq.size());
+   rc |= dev_upload(&dp.btab, bp.tab.data(), bp.tab.size());
+   rc |= dev_upload(&dp.buid, bp.uid.data(), bp.uid.size());
+   rc |= dev_upload(&dp.lidx, lp.data(), lp.size());
+   rc |= dev_upload(&dp.uoff, bp.uoff.data(), bp.uoff.size());
+   rc |= dev_upload(&dp.upos, bp.upos.data(), bp.upos.size());
+   if (rc) { return LAGB_ERR_CUDA; }
+   auto ins = c.plans.emplace(NB, dp);
+   *out = &ins.first->second;
+   return LAGB_OK;
+}
+
 static int ipow(int a, int b) { int r = 1; while (b-- > 0) { r *= a; } return r; }
 
 // ---------------------------------------------------------------------------
@@ -354,9 +386,94 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    return LAGB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// The same solver on the brick schedule (device/mass3d_brick.cuh): the direction update
+// d <- M^-1 r + beta d is formed inside the operator's gather (two buffers, swapped every
+// iteration), the operator writes with plain stores (no zero fill of A d), and the vector
+// work per iteration is the single pass update_xr.  Iterates are those of pcg_run_nc.
+// ---------------------------------------------------------------------------
+template<int NC>
+static int pcg_run_brick(Ctx &c, int comp0, const double *b, double *x, double rel_tol, int max_iter,
+                         bool iterative_mode, int *h_iters)
+{
+   const int64_t n = c.ndofs, cs = n;
+   double *r = c.d_r, *z = c.d_z;
+   double *dcur = c.d_d, *dnxt = c.d_d2;
+   pcg::Prec P; P.dinv = c.d_dinv; P.ess = c.d_essmask; P.comp0 = comp0;
+   const unsigned char *own = c.d_own;
+   const int g = vec_grid(n);
+   if (g*NC > c.part_cap) { set_error("pcg: partial buffer too small"); return LAGB_ERR_STATE; }
+   KernelSet &ks = c.ks;
+   auto reduced = [&](int nblocks, double *tmp, const double *&src, int &nsrc) -> int
+   {
+      if (c.nranks <= 1) { src = c.d_part; nsrc = nblocks; return LAGB_OK; }
+      pcg::reduce_final<NC><<<1, pcg::FB, 0, c.stream>>>(nblocks, c.d_part, tmp);
+      LAGB_LAUNCH_CHECK();
+      int rc = allreduce_sum(c, tmp, NC); if (rc) { return rc; }
+      src = tmp; nsrc = 1;
+      return LAGB_OK;
+   };
+   auto apply = [&](const MassBrickIn &in, bool want_den) -> int
+   {
+      if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
+      int rc = ks.mass_brick(c, NC, in, z, want_den); if (rc) { return rc; }
+      if (c.profile_mass) { int rt = timer_end(c, 4); if (rt) { return rt; } c.mass_launches++; }
+      return halo_sum(c, z, NC);
+   };
+   int rc, nsrc = 0;
+   const double *src = nullptr;
+   if (iterative_mode) { MassBrickIn in; in.x = x; rc = apply(in, false); if (rc) { return rc; } }
+   else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
+   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, P, own, r, dcur, c.d_part, iterative_mode ? 1 : 0);
+   LAGB_LAUNCH_CHECK();
+   rc = reduced(g, c.d_tmp, src, nsrc); if (rc) { return rc; }
+   pcg::finish_init<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, rel_tol, 0.0);   // beta = 0: first direction = M^-1 r
+   LAGB_LAUNCH_CHECK();
+
+   int next_check = std::max(1, c.predicted_iters - 1);
+   bool finished = false;
+   int it = 0;
+   auto poll = [&]() -> int
+   {
+      LAGB_CUDA(cudaMemcpyAsync(c.h_state, c.d_state, sizeof(pcg::State), cudaMemcpyDeviceToHost, c.stream));
+      LAGB_CUDA(cudaStreamSynchronize(c.stream));
+      finished = c.h_state->all_done != 0;
+      return LAGB_OK;
+   };
+   if (c.predicted_iters == 0) { rc = poll(); if (rc) { return rc; } }
+   while (!finished && it < max_iter)
+   {
+      it++;
+      MassBrickIn in; in.r = r; in.dold = dcur; in.dnew = dnxt; in.comp0 = comp0;
+      rc = apply(in, true); if (rc) { return rc; }
+      rc = reduced(c.dt_nblocks, c.d_tmp, src, nsrc); if (rc) { return rc; }
+      pcg::finish_den<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it);
+      LAGB_LAUNCH_CHECK();
+      pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, dnxt, z, P, own, c.d_part);
+      LAGB_LAUNCH_CHECK();
+      rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
+      pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
+      LAGB_LAUNCH_CHECK();
+      std::swap(dcur, dnxt);
+      if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
+   }
+   if (!finished) { rc = poll(); if (rc) { return rc; } }
+   int mx = 0;
+   for (int k = 0; k < NC; k++) { h_iters[k] = c.h_state->iters[k]; mx = std::max(mx, h_iters[k]); }
+   c.predicted_iters = mx;
+   return LAGB_OK;
+}
+
+static bool use_brick(const Ctx &c) { return c.variant == 0 && c.ks.mass_brick != nullptr && c.tune[6] == 0; }
+
 static int pcg_run(Ctx &c, bool l2, int nc, int comp0, const double *b, double *x, double rel_tol,
                    int max_iter, bool iterative_mode, int *h_iters)
 {
+   if (!l2 && use_brick(c))
+   {
+      if (nc == 1) { return pcg_run_brick<1>(c, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters); }
+      if (nc == 3) { return pcg_run_brick<3>(c, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters); }
+   }
    switch (nc)
    {
       case 1: return pcg_run_nc<1>(c, l2, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters);
@@ -409,6 +526,8 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    int rc = 0;
    const size_t NEQ = (size_t)c.NE*c.NQ, D2 = (size_t)c.dim*c.dim;
    rc |= dev_upload(&c.d_map, d->h_h1_map, (size_t)c.NE*c.ND);
+   c.h_map.assign(d->h_h1_map, d->h_h1_map + (size_t)c.NE*c.ND);
+   for (int k = 0; k < 3; k++) { c.elem_grid[k] = d->elem_grid[k]; }
    for (int k = 0; k < c.dim; k++) { c.ness[k] = d->ness[k]; rc |= dev_upload(&c.d_ess[k], d->h_ess[k], (size_t)d->ness[k]); }
    rc |= dev_upload(&c.d_qweights, d->h_qweights, (size_t)c.NQ);
    {
@@ -427,7 +546,7 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
       rc |= dev_upload(&c.d_essmask, em.data(), em.size());
    }
    rc |= dev_alloc(&c.d_r, (size_t)c.ndofs*c.dim); rc |= dev_alloc(&c.d_d, (size_t)c.ndofs*c.dim);
-   rc |= dev_alloc(&c.d_z, (size_t)c.ndofs*c.dim);
+   rc |= dev_alloc(&c.d_z, (size_t)c.ndofs*c.dim); rc |= dev_alloc(&c.d_d2, (size_t)c.ndofs*c.dim);
    rc |= dev_alloc(&c.d_lr, (size_t)c.ndofs_l2); rc |= dev_alloc(&c.d_ld, (size_t)c.ndofs_l2);
    rc |= dev_alloc(&c.d_lz, (size_t)c.ndofs_l2);
    c.part_cap = std::max(c.NE, 148*16)*4 + 64;
@@ -452,8 +571,14 @@ void lagb_ctx_destroy(lagb_ctx *h)
    cudaStreamSynchronize(c.stream);
    void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_inv_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
                    c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinv, c.d_essmask, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
-                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own};
+                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own, c.d_d2};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
+   for (auto &kv : c.plans)
+   {
+      DevPlan &dp = kv.second;
+      void *pp[] = {dp.belem, dp.bnuniq, dp.btab, dp.buid, dp.lidx, dp.uoff, dp.upos};
+      for (void *p : pp) { if (p) { cudaFree(p); } }
+   }
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
    void *hp[] = {c.d_pack_idx, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_send_all, c.d_recv_all};
    for (void *p : hp) { if (p) { cudaFree(p); } }
@@ -518,8 +643,13 @@ int lagb_vmass_mult(lagb_ctx *h, int comp, const double *d_x, double *d_y)
    Ctx &c = h->c;
    if (comp >= c.dim) { set_error("vmass_mult: bad component"); return LAGB_ERR_INVALID; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
-   LAGB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double)*c.ndofs, c.stream));
-   int rc = ks.mass_h1(c, 1, d_x, d_y, false); if (rc) { return rc; }
+   int rc;
+   if (use_brick(c)) { MassBrickIn in; in.x = d_x; rc = ks.mass_brick(c, 1, in, d_y, false); if (rc) { return rc; } }
+   else
+   {
+      LAGB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double)*c.ndofs, c.stream));
+      rc = ks.mass_h1(c, 1, d_x, d_y, false); if (rc) { return rc; }
+   }
    rc = halo_sum(c, d_y, 1); if (rc) { return rc; }
    if (comp >= 0 && c.ness[comp] > 0)
    {
@@ -533,9 +663,30 @@ int lagb_vmass_mult_all(lagb_ctx *h, const double *d_x, double *d_y)
 {
    Ctx &c = h->c;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
-   LAGB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double)*c.ndofs*c.dim, c.stream));
-   int rc = ks.mass_h1(c, c.dim, d_x, d_y, false); if (rc) { return rc; }
+   int rc;
+   if (use_brick(c) && c.dim == 3) { MassBrickIn in; in.x = d_x; rc = ks.mass_brick(c, 3, in, d_y, false); if (rc) { return rc; } }
+   else
+   {
+      LAGB_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double)*c.ndofs*c.dim, c.stream));
+      rc = ks.mass_h1(c, c.dim, d_x, d_y, false); if (rc) { return rc; }
+   }
    return halo_sum(c, d_y, c.dim);
+}
+
+int lagb_host_batch_plan_check(const int32_t *h_map, int NE, int ND, int64_t ndofs, const int32_t grid[3], int NB, int64_t stats[8])
+{
+   BatchPlan bp; std::string err;
+   const int g[3] = {grid ? grid[0] : 0, grid ? grid[1] : 0, grid ? grid[2] : 0}, shape[3] = {0, 0, 0};
+   if (bp.build(h_map, NE, ND, ndofs, g, NB, shape, err)) { set_error(err); return LAGB_ERR_INVALID; }
+   if (bp.self_check(h_map, NE, ndofs, err)) { set_error("batch plan: " + err); return LAGB_ERR_STATE; }
+   if (stats)
+   {
+      stats[0] = bp.nbatch; stats[1] = bp.ncolors; stats[2] = bp.ntab; stats[3] = bp.umax; stats[4] = bp.UP;
+      stats[5] = bp.n_first; stats[6] = bp.brick[0] + 100*bp.brick[1] + 10000*bp.brick[2];
+      int64_t tot = 0; for (int u : bp.nuniq) { tot += u; }
+      stats[7] = tot;
+   }
+   return LAGB_OK;
 }
 
 int lagb_tune_set(lagb_ctx *h, int key, int value)

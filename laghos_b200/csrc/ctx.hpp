@@ -3,6 +3,7 @@
 #include "../../include/laghos_b200.h"
 #include "device/pcg.cuh"
 #include <cuda_runtime.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -18,10 +19,30 @@ extern int64_t g_launch_count;
 
 struct Ctx;
 
+// input of the brick mass apply (device/mass3d_brick.cuh): plain x, or the fused PCG direction
+// update d_new = M^-1 r + beta d_old (x == nullptr)
+struct MassBrickIn
+{
+   const double *x = nullptr;
+   const double *r = nullptr, *dold = nullptr; double *dnew = nullptr;
+   int comp0 = 0;
+};
+
+// device copy of a host BatchPlan (host/batch_plan.hpp)
+struct DevPlan
+{
+   int NB = 0, UP = 0, nbatch = 0, ncolors = 0, ntab = 0;
+   std::vector<int> color_begin;
+   int *belem = nullptr, *bnuniq = nullptr, *btab = nullptr; uint32_t *buid = nullptr;
+   uint16_t *lidx = nullptr, *uoff = nullptr, *upos = nullptr;
+};
+
 // per-(DIM,D1D,Q1D) launchers
 struct KernelSet
 {
    int (*mass_h1)(Ctx&, int nc, const double *x, double *y, bool with_den) = nullptr; // y += M x (nc comps, byNODES stride)
+   // y = M x without atomics (coloured brick schedule); nullptr where not instantiated
+   int (*mass_brick)(Ctx&, int nc, const MassBrickIn &in, double *y, bool with_den) = nullptr;
    int (*mass_diag)(Ctx&, double *diag) = nullptr;
    int (*mass_l2)(Ctx&, const double *x, double *y) = nullptr;
    int (*force_mult)(Ctx&, const double *e, double *v) = nullptr;       // v += F e
@@ -61,6 +82,11 @@ struct Ctx
    double *d_diag = nullptr, *d_dinv = nullptr;      // [ndofs] mass diagonal and its inverse
    unsigned char *d_essmask = nullptr;               // [ndofs] bit c: essential for component c
    double *d_r = nullptr, *d_d = nullptr, *d_z = nullptr;      // [dim*ndofs]
+   double *d_d2 = nullptr;                                     // second search-direction buffer (fused brick PCG)
+   int elem_grid[3] = {0, 0, 0};                               // structured element grid hint (0 = none)
+   std::vector<int> h_map;                                     // host copy of the gather map (schedules are built lazily)
+   std::map<const void*, size_t> smem_optin;                   // kernels whose dynamic shared memory opt-in is set on this device
+   std::map<int, DevPlan> plans;                               // brick schedules by (NB | shape key)
    double *d_lr = nullptr, *d_ld = nullptr, *d_lz = nullptr;   // [ndofs_l2]
    double *d_part = nullptr; int part_cap = 0;                 // reduction partials
    double *d_tmp = nullptr;                                    // [8] reduced scalars
@@ -99,6 +125,8 @@ int timer_end(Ctx &c, int which);
 int halo_sum(Ctx &c, double *v, int nc);              // sum shared dofs across ranks (no-op for 1 rank)
 int allreduce_sum(Ctx &c, double *d_vals, int n);     // in-stream
 int allreduce_min(Ctx &c, double *d_vals, int n);
+
+int get_plan(Ctx &c, int NB, const DevPlan **out);    // brick schedule for NB elements per batch (built on first use)
 
 KernelSet make_generic_kernels(int dim, int D1D, int Q1D);
 bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D);

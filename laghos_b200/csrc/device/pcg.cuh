@@ -175,6 +175,7 @@ __global__ void finish_init(State *st, const double *part, int nblocks, double r
       st->nom[c] = nom;
       st->iters[c] = 0;
       st->done[c] = 0;
+      st->beta[c] = 0.0; st->alpha[c] = 0.0;
       if (nom < 0.0) { st->done[c] = 1; }   // not positive definite: MFEM returns, final_iter = 0
       const double r0 = fmax(nom*rel_tol*rel_tol, abs_tol*abs_tol);
       st->r0[c] = r0;

@@ -2,15 +2,20 @@
 #include "ctx.hpp"
 #include <algorithm>
 #include "device/mass3d.cuh"
-#include "device/mass3d_shfl.cuh"
+#include "device/mass3d_brick.cuh"
 #include "device/staged3d.cuh"
 
 namespace lagb {
 
+// opt-in dynamic shared memory: the attribute is per device, so it is tracked per context (one
+// context = one device), not per process
 template<typename K>
-static int set_smem(K kern, size_t bytes)
+static int set_smem(Ctx &c, K kern, size_t bytes)
 {
+   size_t &have = c.smem_optin[(const void*)kern];
+   if (have >= bytes && have != 0) { return LAGB_OK; }
    LAGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+   have = bytes;
    return LAGB_OK;
 }
 
@@ -22,6 +27,8 @@ template<int D1D, int Q1D, int NB1, int MINB1, int NB3, int MINB3, int NTQ, int 
 struct TunedLaunch3D
 {
    using Tab = DevTables<D1D,Q1D>;
+   // elements per batch of the brick mass apply (orders without tuning variants)
+   static constexpr int NBB = (D1D <= 2) ? 32 : (D1D == 3) ? 16 : (D1D <= 5) ? 8 : 4;
    static const Tab &tab(Ctx &c) { return *reinterpret_cast<const Tab*>(c.tab_blob.data()); }
 
    template<int NC, bool WITH_DEN, int NB, int MINB, bool DS = false, bool DG = false>
@@ -29,24 +36,10 @@ struct TunedLaunch3D
    {
       using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
       auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB,DS,DG>;
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
+      { int rc = set_smem(c, kern, Cfg::SMEM_BYTES); if (rc) { return rc; } }
       const int grid = (c.NE + NB - 1)/NB;
       if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
       kern<<<grid, Cfg::T, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part);
-      LAGB_LAUNCH_CHECK();
-      if (WITH_DEN) { c.dt_nblocks = grid; }
-      return LAGB_OK;
-   }
-   // experimental shuffle hand-off variant (device/mass3d_shfl.cuh), D1D = 4 only
-   template<int NC, bool WITH_DEN, int NB, int MINB>
-   static int mass_launch_shfl(Ctx &c, const double *x, double *y)
-   {
-      static_assert((NB*4) % 32 == 0, "a component group must be whole warps");
-      auto kern = tuned::mass3d_shfl<Q1D,NB,NC,WITH_DEN,MINB>;
-      const int grid = (c.NE + NB - 1)/NB;
-      if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d_shfl: partial buffer too small"); return LAGB_ERR_STATE; }
-      kern<<<grid, NC*NB*4, 0, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part);
       LAGB_LAUNCH_CHECK();
       if (WITH_DEN) { c.dt_nblocks = grid; }
       return LAGB_OK;
@@ -62,8 +55,6 @@ struct TunedLaunch3D
             case 2: return mass_launch_v<NC,WITH_DEN,16,3,true,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
-            case 5: if constexpr ((Q1D*Q1D) % 4 == 0) { return mass_launch_shfl<NC,WITH_DEN,8,4>(c, x, y); } break;
-            case 6: if constexpr ((Q1D*Q1D) % 4 == 0) { return mass_launch_shfl<NC,WITH_DEN,8,3>(c, x, y); } break;
          }
          return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants*.txt): 351 us
       }
@@ -81,6 +72,71 @@ struct TunedLaunch3D
       // direct gather / scatter for the low orders; staged through shared memory where registers are tight
       return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3,(D1D <= 3),(D1D <= 3)>(c, x, y);
    }
+   // ---- brick schedule (device/mass3d_brick.cuh): one launch per colour, programmatic dependent launch ----
+   template<int NC, bool WITH_DEN, bool FUSE, int NB, int MINB>
+   static int brick_launch_v(Ctx &c, const MassBrickIn &in, double *y)
+   {
+      using Cfg = tuned::MassBrickCfg<D1D,Q1D,NB,NC>;
+      const DevPlan *pl = nullptr;
+      int rc = get_plan(c, NB, &pl); if (rc) { return rc; }
+      auto kern = tuned::mass3d_brick<D1D,Q1D,NB,NC,WITH_DEN,FUSE,MINB>;
+      const size_t bytes = Cfg::smem_bytes(pl->UP);
+      rc = set_smem(c, kern, bytes); if (rc) { return rc; }
+      if (WITH_DEN && pl->nbatch*NC > c.part_cap) { set_error("mass3d_brick: partial buffer too small"); return LAGB_ERR_STATE; }
+      tuned::BrickArgs a;
+      a.UP = pl->UP; a.NE = c.NE; a.cstride = c.ndofs;
+      a.belem = pl->belem; a.bnuniq = pl->bnuniq; a.buid = pl->buid; a.btab = pl->btab;
+      a.lidx = pl->lidx; a.uoff = pl->uoff; a.upos = pl->upos;
+      a.Dq = c.d_massD; a.x = in.x; a.r = in.r; a.dold = in.dold; a.dnew = in.dnew;
+      a.dinv = c.d_dinv; a.ess = c.d_essmask; a.st = c.d_state; a.comp0 = in.comp0;
+      a.y = y; a.den_part = c.d_part;
+      for (int col = 0; col < pl->ncolors; col++)
+      {
+         a.batch0 = pl->color_begin[col]; a.nbatch_launch = pl->color_begin[col + 1] - a.batch0;
+         if (a.nbatch_launch <= 0) { continue; }
+         cudaLaunchConfig_t cfg = {};
+         cfg.gridDim = dim3((unsigned)a.nbatch_launch); cfg.blockDim = dim3(Cfg::T); cfg.dynamicSmemBytes = bytes; cfg.stream = c.stream;
+         cudaLaunchAttribute at[1];
+         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+         at[0].val.programmaticStreamSerializationAllowed = 1;
+         cfg.attrs = at; cfg.numAttrs = (col > 0 && c.tune[5] == 0) ? 1 : 0;   // colour 0 waits for everything before it
+         LAGB_CUDA(cudaLaunchKernelEx(&cfg, kern, tab(c), a));
+         LAGB_LAUNCH_CHECK();
+      }
+      if (WITH_DEN) { c.dt_nblocks = pl->nbatch; }
+      return LAGB_OK;
+   }
+   template<int NC, bool WITH_DEN, bool FUSE>
+   static int brick_launch(Ctx &c, const MassBrickIn &in, double *y)
+   {
+      if constexpr (D1D == 4)   // tuning variants (lagb_tune_set key 4): elements per batch / resident CTAs
+      {
+         switch (c.tune[4])
+         {
+            case 1: return brick_launch_v<NC,WITH_DEN,FUSE,8,3>(c, in, y);
+            case 2: return brick_launch_v<NC,WITH_DEN,FUSE,16,2>(c, in, y);
+            case 3: return brick_launch_v<NC,WITH_DEN,FUSE,8,5>(c, in, y);
+            case 4: return brick_launch_v<NC,WITH_DEN,FUSE,16,1>(c, in, y);
+         }
+         return brick_launch_v<NC,WITH_DEN,FUSE,8,4>(c, in, y);
+      }
+      return brick_launch_v<NC,WITH_DEN,FUSE,NBB,1>(c, in, y);
+   }
+   static int mass_brick(Ctx &c, int nc, const MassBrickIn &in, double *y, bool with_den)
+   {
+      const bool fuse = in.x == nullptr;
+      if (nc == 3)
+      {
+         if (fuse) { return with_den ? brick_launch<3,true,true>(c, in, y) : brick_launch<3,false,true>(c, in, y); }
+         return with_den ? brick_launch<3,true,false>(c, in, y) : brick_launch<3,false,false>(c, in, y);
+      }
+      if (nc == 1)
+      {
+         if (fuse) { return with_den ? brick_launch<1,true,true>(c, in, y) : brick_launch<1,false,true>(c, in, y); }
+         return with_den ? brick_launch<1,true,false>(c, in, y) : brick_launch<1,false,false>(c, in, y);
+      }
+      set_error("mass3d_brick: nc must be 1 or 3"); return LAGB_ERR_INVALID;
+   }
    static int mass_h1(Ctx &c, int nc, const double *x, double *y, bool with_den)
    {
       if (nc == 3) { return with_den ? mass_launch<3,true>(c, x, y) : mass_launch<3,false>(c, x, y); }
@@ -93,8 +149,7 @@ struct TunedLaunch3D
       static_assert(NTQ % 32 == 0 && NTF % 32 == 0, "CTA sizes must be whole warps");
       using Cfg = tuned::QUpd3DCfg<D1D,Q1D>;
       auto kern = tuned::qupdate3d<D1D,Q1D,NTQ,MINB>;
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, Cfg::SMEM_BYTES); if (rc) { return rc; } attr_set = true; }
+      { int rc = set_smem(c, kern, Cfg::SMEM_BYTES); if (rc) { return rc; } }
       const int grid = c.NE;
       kern<<<grid, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
                                                     c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_dt);
@@ -124,8 +179,7 @@ struct TunedLaunch3D
       using Cfg = tuned::Force3DCfg<D1D,Q1D>;
       auto kern = tuned::force3d<D1D,Q1D,NB,NT,PF>;
       constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + (PF ? 9*Cfg::NQ : 0));
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
@@ -136,8 +190,7 @@ struct TunedLaunch3D
       using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
       auto kern = tuned::forcet3d<D1D,Q1D,NB,NT,PF>;
       constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + (PF ? Cfg::S_PF : 0));
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
@@ -177,8 +230,7 @@ struct TunedLaunch3D
       constexpr int NB = (Q1D <= 2) ? 64 : (Q1D <= 4) ? 32 : (Q1D <= 6) ? 16 : (Q1D <= 8) ? 8 : 4, NT = 256;
       auto kern = tuned::massl2_3d<D1D,Q1D,NB,NT>;
       constexpr size_t bytes = sizeof(double)*(size_t)NB*Cfg::PER_ELEM;
-      static bool attr_set = false;
-      if (!attr_set) { int rc = set_smem(kern, bytes); if (rc) { return rc; } attr_set = true; }
+      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.d_massD, x, y);
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
@@ -186,7 +238,7 @@ struct TunedLaunch3D
    static void install(KernelSet &ks)
    {
       ks.mass_h1 = &mass_h1; ks.qupdate = &qupdate; ks.force_mult = &force_mult;
-      ks.force_mult_t = &force_mult_t; ks.mass_l2 = &mass_l2;
+      ks.force_mult_t = &force_mult_t; ks.mass_l2 = &mass_l2; ks.mass_brick = &mass_brick;
       ks.tuned_mass = true;
    }
 };

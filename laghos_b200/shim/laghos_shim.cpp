@@ -332,6 +332,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
    d.h_B = P.tab.B.data(); d.h_G = P.tab.G.data(); d.h_BL = P.tab.BL.data();
    d.h_qweights = P.qweights.data(); d.h_gamma = P.gamma.data();
    d.use_visc = P.use_visc; d.use_vort = P.use_vort; d.device = opt->device; d.kernel_variant = opt->kernel_variant;
+   for (int k = 0; k < 3; k++) { d.elem_grid[k] = P.nloc[k]; }   // Cartesian block, lexicographic element numbering
    lagb_ctx *ctx = nullptr;
    LAGHOS_CHECK(lagb_ctx_create(&ctx, &d, nullptr));
    if (nranks > 1)

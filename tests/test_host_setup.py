@@ -126,27 +126,106 @@ def test_oracle_energies(built):
     assert abs(r["energy_init"] - r["energy_final"]) < 1e-9 * r["energy_init"]   # smooth Taylor-Green: RK4 conserves to ~1e-11
 
 
-def test_quad_transpose_emulation():
-    """Index logic of the experimental shuffle hand-off (device/mass3d_shfl.cuh, quad_transpose): a two-step
-    xor butterfly over 4 lanes with compile-time register indices transposes the 4 x 4 block matrix
-    (lane j, slot m) <- (lane m, column 4k + j) and is an involution.  Emulated lane by lane."""
-    NK = 9
-    V = np.array([[100.0 * j + col for col in range(4 * NK)] for j in range(4)])
+# ---- brick schedule of the mass apply (host/batch_plan.hpp) ----
+@pytest.mark.parametrize("mesh,rs,ok,grid_hint,nb", [
+    ("cube01_hex", 2, 3, True, 8), ("cube01_hex", 2, 3, True, 16), ("cube01_hex", 1, 2, True, 16),
+    ("box01_hex", 1, 3, True, 8), ("cube01_hex", 2, 3, False, 8), ("cube01_hex", 0, 4, True, 8),
+    ("cube01_hex", 1, 1, False, 32)])
+def test_batch_plan_invariants(built, mesh, rs, ok, grid_hint, nb):
+    """Every element scheduled once, colours conflict-free, one first writer per dof (checked in C++),
+    plus the counts a Cartesian brick must have."""
+    import ctypes as C
+    from laghos_b200.api import Problem
+    P = Problem(mesh, rs, 1, ok, ok - 1)
+    mp = np.ascontiguousarray(P.h1_map, dtype=np.int32)
+    ne = [(int(P.info.n1[k]) - 1) // (P.D1D - 1) for k in range(3)]
+    grid = (C.c_int32 * 3)(*(ne if grid_hint else [0, 0, 0]))
+    stats = (C.c_int64 * 8)()
+    rc = P.lib.lagb_host_batch_plan_check(mp.ctypes.data_as(C.POINTER(C.c_int32)), P.NE, P.ND, P.ndofs_h1, grid, nb, stats)
+    assert rc == 0, P.lib.lagb_last_error().decode()
+    nbatch, ncolors, ntab, umax, UP, nfirst, shape, tot = [int(v) for v in stats]
+    assert nfirst == P.ndofs_h1 and UP >= umax and UP % 32 == 0
+    if grid_hint:
+        b = [shape % 100, (shape // 100) % 100, shape // 10000]
+        assert b[0] * b[1] * b[2] <= nb
+        full = all(ne[k] % b[k] == 0 for k in range(3))
+        if full:
+            assert umax == np.prod([b[k] * ok + 1 for k in range(3)])
+            assert nbatch == np.prod([ne[k] // b[k] for k in range(3)])
+            assert ntab == 1            # all bricks share one index table
+        assert ncolors <= 8
+    else:
+        assert nbatch == (P.NE + nb - 1) // nb
 
-    def transpose(V):
-        V = V.copy()
-        for p in (0, 2):
-            for k in range(NK):
-                send = [V[j, 4 * k + p] if (j & 1) else V[j, 4 * k + p + 1] for j in range(4)]
-                for j in range(4):
-                    V[j, 4 * k + p + (0 if j & 1 else 1)] = send[j ^ 1]
-        for s in (0, 1):
-            for k in range(NK):
-                send = [V[j, 4 * k + s] if (j & 2) else V[j, 4 * k + 2 + s] for j in range(4)]
-                for j in range(4):
-                    V[j, 4 * k + (s if j & 2 else 2 + s)] = send[j ^ 2]
-        return V
 
-    T = transpose(V)
-    assert all(T[j, 4 * k + m] == 100.0 * m + 4 * k + j for j in range(4) for k in range(NK) for m in range(4))
-    assert np.array_equal(transpose(T), V)
+def test_batch_plan_apply_emulation(built):
+    """numpy emulation of the coloured schedule: first writers store, later colours add; the result
+    equals the plain E^t E sum and no zero fill is needed."""
+    from laghos_b200.api import Problem
+    P = Problem("cube01_hex", 1, 1, 3, 2)
+    mp = P.h1_map.reshape(P.NE, P.ND)
+    rng = np.random.default_rng(5)
+    ev = rng.uniform(-1, 1, (P.NE, P.ND))
+    ref = np.zeros(P.ndofs_h1)
+    np.add.at(ref, mp.ravel(), ev.ravel())
+    # bricks 2x2x2 with parity colours, as BatchPlan builds them
+    n = [(int(P.info.n1[k]) - 1) // (P.D1D - 1) for k in range(3)]
+    y = np.full(P.ndofs_h1, np.nan)      # garbage: the schedule never reads before the first writer stored
+    bricks = {}
+    for e in range(P.NE):
+        ex, ey, ez = e % n[0], (e // n[0]) % n[1], e // (n[0] * n[1])
+        kb = (ex // 2, ey // 2, ez // 2)
+        bricks.setdefault(kb, []).append(e)
+    mincol = {}
+    for kb, els in bricks.items():
+        col = (kb[0] & 1) | ((kb[1] & 1) << 1) | ((kb[2] & 1) << 2)
+        for d in np.unique(mp[els]):
+            mincol[d] = min(mincol.get(d, 99), col)
+    for col in range(8):
+        for kb, els in bricks.items():
+            if ((kb[0] & 1) | ((kb[1] & 1) << 1) | ((kb[2] & 1) << 2)) != col:
+                continue
+            u, inv = np.unique(mp[els].ravel(), return_inverse=True)
+            s = np.zeros(len(u))
+            np.add.at(s, inv, ev[els].ravel())
+            for j, d in enumerate(u):
+                if mincol[d] == col:
+                    y[d] = s[j]
+                else:
+                    y[d] += s[j]
+    assert np.all(np.isfinite(y))
+    assert np.max(np.abs(y - ref)) < 1e-14
+
+
+# ---- 1D tables against closed forms that do not share code with host/fe_tables.hpp ----
+def test_tables_closed_form(built):
+    """Gauss-Legendre points/weights (numpy), Gauss-Lobatto nodes (roots of (1-x^2) P'_{p}), nodal
+    Lagrange values/derivatives (numpy polynomial arithmetic) and Bernstein values for orders 1-5."""
+    from numpy.polynomial import legendre as L, polynomial as Pn
+    from math import comb
+    from laghos_b200.api import Problem
+    for ok, ot in [(1, 0), (2, 1), (3, 2), (4, 3), (5, 4)]:
+        P = Problem("cube01_hex", 0, 1, ok, ot)
+        Q, D, Lb = P.Q1D, P.D1D, P.L1D
+        qx, qw = P.table(3, Q), P.table(4, Q)
+        gx, gw = L.leggauss(Q)
+        assert np.max(np.abs(qx - 0.5 * (gx + 1))) < 1e-15 and np.max(np.abs(qw - 0.5 * gw)) < 1e-15
+        # GLL nodes on [0,1]
+        if ok == 1:
+            nodes = np.array([0.0, 1.0])
+        else:
+            c = np.zeros(ok + 1); c[ok] = 1.0
+            inner = np.sort(L.legroots(L.legder(c)))
+            nodes = 0.5 * (np.concatenate([[-1.0], inner, [1.0]]) + 1)
+        B = P.table(0, Q * D).reshape(D, Q)
+        G = P.table(1, Q * D).reshape(D, Q)
+        for d in range(D):
+            others = np.delete(nodes, d)
+            den = np.prod(nodes[d] - others)
+            val = np.array([np.prod(x - others) for x in qx]) / den            # product form (well conditioned)
+            der = np.array([sum(np.prod(x - np.delete(others, k)) for k in range(len(others))) for x in qx]) / den
+            assert np.max(np.abs(B[d] - val)) < 5e-15
+            assert np.max(np.abs(G[d] - der)) < 2e-13
+        BL = P.table(2, Q * Lb).reshape(Lb, Q)
+        for l in range(Lb):
+            assert np.max(np.abs(BL[l] - comb(ot, l) * qx ** l * (1 - qx) ** (ot - l))) < 1e-15

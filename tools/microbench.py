@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--force-variants", default="0,1,2,3,4")
     ap.add_argument("--q-variants", default="0,1,2")
     ap.add_argument("--mass1-variants", default="0")
+    ap.add_argument("--brick-variants", default="0,1,2,3,4")
+    ap.add_argument("--only", default="", help="comma list of sections: q,force,mass,l2,pcg (default all)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -72,13 +74,14 @@ def main():
         print(f"{name:38s} {us:10.1f} us  {gbytes:7.3f} GB  {bw:8.1f} GB/s  {100 * bw / peak:5.1f}% of {peak:.0f}{chk}", flush=True)
 
     dim = P.dim
-    for var in [int(s) for s in args.q_variants.split(",")]:
+    only = set(args.only.split(",")) if args.only else {"q", "force", "mass", "l2", "pcg"}
+    for var in ([int(s) for s in args.q_variants.split(",")] if "q" in only else []):
         c.tune(2, var)
         report(f"qupdate (fused) variant {var}", timeit(lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
                8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)), c.qdata(0))
     c.tune(2, 0)
     ye = c.empty(nl)
-    for var in [int(s) for s in args.force_variants.split(",")]:
+    for var in ([int(s) for s in args.force_variants.split(",")] if "force" in only else []):
         c.tune(1, var)
         report(f"force_mult variant {var}", timeit(lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
                8e-9 * (dim * dim * NE * NQ + nl + dim * nd), yv)
@@ -86,18 +89,32 @@ def main():
                8e-9 * (dim * dim * NE * NQ + nl + dim * nd), ye)
     c.tune(1, 0)
     y1 = c.empty(nd)
-    for var in [int(s) for s in args.mass1_variants.split(",")]:
+    # brick schedule (no atomics): key 4 = variant, key 5 = 1 disables programmatic dependent launch
+    for var in ([int(s) for s in args.brick_variants.split(",")] if "mass" in only else []):
+        c.tune(4, var)
+        for pdl_off in (0, 1):
+            c.tune(5, pdl_off)
+            report(f"vmass_mult_all brick variant {var} pdl {1 - pdl_off}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
+                   8e-9 * (NE * NQ + 2 * dim * nd), yv)
+        c.tune(5, 0)
+        report(f"vmass_mult (1 comp) brick variant {var}", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
+               8e-9 * (NE * NQ + 2 * nd), y1)
+    c.tune(4, 0)
+    c.tune(6, 1)   # legacy atomic-scatter kernels
+    for var in ([int(s) for s in args.mass1_variants.split(",")] if "mass" in only else []):
         c.tune(3, var)
         report(f"vmass_mult (1 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
                8e-9 * (NE * NQ + 2 * nd), y1)
     c.tune(3, 0)
-    for var in [int(s) for s in args.mass_variants.split(",")]:
+    for var in ([int(s) for s in args.mass_variants.split(",")] if "mass" in only else []):
         c.tune(0, var)
         report(f"vmass_mult_all (3 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
                8e-9 * (NE * NQ + 2 * dim * nd), yv)
     c.tune(0, 0)
-    report("emass_mult (L2)", timeit(lambda: c.lib.lagb_emass_mult(c.h, c._p(e), c._p(ye))), 8e-9 * (NE * NQ + 2 * nl))
-    if args.no_pcg:
+    c.tune(6, 0)
+    if "l2" in only:
+        report("emass_mult (L2)", timeit(lambda: c.lib.lagb_emass_mult(c.h, c._p(e), c._p(ye))), 8e-9 * (NE * NQ + 2 * nl))
+    if args.no_pcg or "pcg" not in only:
         c.close()
         return
     b = c.dev(rng.uniform(-1, 1, nv))
@@ -107,10 +124,13 @@ def main():
         xs.zero_()
         c.pcg_vmass_all(b, xs)
 
-    us = timeit(pcg, 3)
-    _, its = c.pcg_vmass_all(b, c.zeros(nv))
-    nit = max(its)
-    print(f"pcg_vmass_all: {us:.1f} us for {its} iterations -> {us / (nit + 1):.1f} us per iteration", flush=True)
+    for legacy in (0, 1):
+        c.tune(6, legacy)
+        us = timeit(pcg, 3)
+        _, its = c.pcg_vmass_all(b, c.zeros(nv))
+        nit = max(its)
+        print(f"pcg_vmass_all ({'legacy' if legacy else 'brick'}): {us:.1f} us for {its} iterations -> {us / (nit + 1):.1f} us per iteration", flush=True)
+    c.tune(6, 0)
     bl = c.dev(rng.uniform(-1, 1, nl))
     us = timeit(lambda: c.cg_emass(bl), 3)
     _, it2 = c.cg_emass(bl)
