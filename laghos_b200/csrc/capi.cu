@@ -258,19 +258,51 @@ template<typename T> static int dev_upload(T **p, const T *h, size_t n)
 // map on first use, uploaded once (host/batch_plan.hpp).
 int get_plan(Ctx &c, int NB, const DevPlan **out)
 {
-   auto it = c.plans.find(NB);
+   const int shape_sel = c.tune[7];
+   const int key = NB | (shape_sel << 16);
+   auto it = c.plans.find(key);
    if (it != c.plans.end()) { *out = &it->second; return LAGB_OK; }
    BatchPlan bp; std::string err;
-   const int shape[3] = {0, 0, 0};
+   int shape[3] = {0, 0, 0};
+   if (shape_sel > 0 && c.elem_grid[0] > 0)
+   {
+      // x-long bricks: rows of (D1D-1)*bx + 1 contiguous L-vector entries per lattice row
+      int bx = (shape_sel == 2) ? NB : std::min(NB, 4), rem = NB/bx, by = std::min(rem, 2), bz = rem/by;
+      while (bx > c.elem_grid[0] && bx > 1) { bx /= 2; }
+      shape[0] = bx; shape[1] = by; shape[2] = bz;
+      if (by > c.elem_grid[1] || bz > c.elem_grid[2] || bx*by*bz > NB) { shape[0] = shape[1] = shape[2] = 0; }
+   }
    if (bp.build(c.h_map.data(), c.NE, c.ND, c.ndofs, c.elem_grid, NB, shape, err)) { set_error(err); return LAGB_ERR_INVALID; }
    DevPlan dp;
    dp.NB = NB; dp.UP = bp.UP; dp.nbatch = bp.nbatch; dp.ncolors = bp.ncolors; dp.ntab = bp.ntab; dp.color_begin = bp.color_begin;
+   for (int k = 0; k < 3; k++) { dp.brick[k] = bp.brick[k]; }
    // lidx rows padded to a multiple of 8 entries (16-byte vector loads)
    const int NDP = ((c.ND + 7)/8)*8;
    std::vector<uint16_t> lp((size_t)bp.ntab*NB*NDP, 0);
    for (int t = 0; t < bp.ntab; t++)
       for (int e = 0; e < NB; e++)
          for (int i = 0; i < c.ND; i++) { lp[((size_t)t*NB + e)*NDP + i] = bp.lidx[((size_t)t*NB + e)*c.ND + i]; }
+   // fixed-width contribution table of the second brick kernel: plane slot (e*D1D + dz)*PLANE + dxy
+   // of every element-local dof that maps to the unique slot (3D only)
+   std::vector<uint16_t> uc;
+   if (c.dim == 3)
+   {
+      const int DD = c.D1D*c.D1D, QQ = c.Q1D*c.Q1D, PLANE = (std::max(QQ, DD) | 1);
+      uc.assign((size_t)bp.ntab*bp.UP*8, (uint16_t)0xffff);
+      bool ok = (size_t)NB*c.D1D*PLANE < 0xffff;
+      for (int t = 0; t < bp.ntab && ok; t++)
+         for (int s = 0; s < bp.UP && ok; s++)
+         {
+            const int p0 = bp.uoff[(size_t)t*(bp.UP + 1) + s], p1 = bp.uoff[(size_t)t*(bp.UP + 1) + s + 1];
+            if (p1 - p0 > 8) { ok = false; break; }
+            for (int p = p0; p < p1; p++)
+            {
+               const int pos = bp.upos[(size_t)t*NB*c.ND + p], e = pos / c.ND, i = pos % c.ND;
+               uc[((size_t)t*bp.UP + s)*8 + (p - p0)] = (uint16_t)((e*c.D1D + i / DD)*PLANE + i % DD);
+            }
+         }
+      if (!ok) { uc.clear(); }
+   }
    int rc = 0;
    rc |= dev_upload(&dp.belem, bp.elem.data(), bp.elem.size());
    rc |= dev_upload(&dp.bnuniq, bp.nuniq.data(), bp.nuniq.size());
@@ -279,8 +311,9 @@ int get_plan(Ctx &c, int NB, const DevPlan **out)
    rc |= dev_upload(&dp.lidx, lp.data(), lp.size());
    rc |= dev_upload(&dp.uoff, bp.uoff.data(), bp.uoff.size());
    rc |= dev_upload(&dp.upos, bp.upos.data(), bp.upos.size());
+   if (!uc.empty()) { rc |= dev_upload(&dp.ucon, uc.data(), uc.size()); }
    if (rc) { return LAGB_ERR_CUDA; }
-   auto ins = c.plans.emplace(NB, dp);
+   auto ins = c.plans.emplace(key, dp);
    *out = &ins.first->second;
    return LAGB_OK;
 }
@@ -464,7 +497,8 @@ static int pcg_run_brick(Ctx &c, int comp0, const double *b, double *x, double r
    return LAGB_OK;
 }
 
-static bool use_brick(const Ctx &c) { return c.variant == 0 && c.ks.mass_brick != nullptr && c.tune[6] == 0; }
+// tune[6]: 0 = default path, 1 = legacy atomic scatter, 2 = brick v1, 3 = brick v2
+static bool use_brick(const Ctx &c) { return c.variant == 0 && c.ks.mass_brick != nullptr && c.tune[6] >= 2; }
 
 static int pcg_run(Ctx &c, bool l2, int nc, int comp0, const double *b, double *x, double rel_tol,
                    int max_iter, bool iterative_mode, int *h_iters)
@@ -576,7 +610,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (auto &kv : c.plans)
    {
       DevPlan &dp = kv.second;
-      void *pp[] = {dp.belem, dp.bnuniq, dp.btab, dp.buid, dp.lidx, dp.uoff, dp.upos};
+      void *pp[] = {dp.belem, dp.bnuniq, dp.btab, dp.buid, dp.lidx, dp.uoff, dp.upos, dp.ucon};
       for (void *p : pp) { if (p) { cudaFree(p); } }
    }
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
@@ -691,7 +725,7 @@ int lagb_host_batch_plan_check(const int32_t *h_map, int NE, int ND, int64_t ndo
 
 int lagb_tune_set(lagb_ctx *h, int key, int value)
 {
-   if (key < 0 || key >= 8) { set_error("tune_set: bad key"); return LAGB_ERR_INVALID; }
+   if (key < 0 || key >= 16) { set_error("tune_set: bad key"); return LAGB_ERR_INVALID; }
    h->c.tune[key] = value;
    return LAGB_OK;
 }

@@ -35,6 +35,8 @@ struct DevPlan
    std::vector<int> color_begin;
    int *belem = nullptr, *bnuniq = nullptr, *btab = nullptr; uint32_t *buid = nullptr;
    uint16_t *lidx = nullptr, *uoff = nullptr, *upos = nullptr;
+   uint16_t *ucon = nullptr;          // [ntab][UP][8] fixed-width contribution table (plane slots), nullptr if a dof has > 8
+   int brick[3] = {0, 0, 0};
 };
 
 // per-(DIM,D1D,Q1D) launchers
@@ -99,7 +101,10 @@ struct Ctx
    double h0 = 0.0;
    bool setup_done = false;
    int dt_nblocks = 0;
-   int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // lagb_tune_set: [0] mass3d NC=3 variant
+   // lagb_tune_set: [0] legacy mass3d NC=3 variant, [1] force, [2] qupdate, [3] legacy mass3d NC=1, [4] brick launch
+   // variant, [5] 1 = no programmatic dependent launch, [6] mass path (0 default, 1 legacy atomic, 2 brick v1, 3 brick v2),
+   // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil)
+   int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing
    Timer timer; int64_t H1iter = 0, L2iter = 0, quad_tstep = 0;
@@ -126,7 +131,7 @@ int halo_sum(Ctx &c, double *v, int nc);              // sum shared dofs across 
 int allreduce_sum(Ctx &c, double *d_vals, int n);     // in-stream
 int allreduce_min(Ctx &c, double *d_vals, int n);
 
-int get_plan(Ctx &c, int NB, const DevPlan **out);    // brick schedule for NB elements per batch (built on first use)
+int get_plan(Ctx &c, int NB, const DevPlan **out);    // brick schedule for NB elements per batch and the shape c.tune[7] (built on first use)
 
 KernelSet make_generic_kernels(int dim, int D1D, int Q1D);
 bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D);

@@ -106,17 +106,76 @@ struct TunedLaunch3D
       if (WITH_DEN) { c.dt_nblocks = pl->nbatch; }
       return LAGB_OK;
    }
+   // second brick kernel (slice/column/slice compute on the deduplicated gather)
+   template<int NC, bool WITH_DEN, bool FUSE, int NB, int MINB, bool DBULK>
+   static int brick2_launch_v(Ctx &c, const MassBrickIn &in, double *y)
+   {
+      using Cfg = tuned::MassBrick2Cfg<D1D,Q1D,NB,NC>;
+      const DevPlan *pl = nullptr;
+      int rc = get_plan(c, NB, &pl); if (rc) { return rc; }
+      if (!pl->ucon) { set_error("mass3d_brick2: a dof has more than 8 contributions inside one batch"); return LAGB_ERR_STATE; }
+      auto kern = tuned::mass3d_brick2<D1D,Q1D,NB,NC,WITH_DEN,FUSE,MINB,DBULK>;
+      const size_t bytes = Cfg::smem_bytes(pl->UP, DBULK);
+      rc = set_smem(c, kern, bytes); if (rc) { return rc; }
+      if (WITH_DEN && pl->nbatch*NC > c.part_cap) { set_error("mass3d_brick2: partial buffer too small"); return LAGB_ERR_STATE; }
+      tuned::BrickArgs a;
+      a.UP = pl->UP; a.NE = c.NE; a.cstride = c.ndofs;
+      a.belem = pl->belem; a.bnuniq = pl->bnuniq; a.buid = pl->buid; a.btab = pl->btab;
+      a.lidx = pl->lidx; a.uoff = pl->uoff; a.upos = pl->upos; a.ucon = pl->ucon;
+      a.Dq = c.d_massD; a.x = in.x; a.r = in.r; a.dold = in.dold; a.dnew = in.dnew;
+      a.dinv = c.d_dinv; a.ess = c.d_essmask; a.st = c.d_state; a.comp0 = in.comp0;
+      a.y = y; a.den_part = c.d_part;
+      for (int col = 0; col < pl->ncolors; col++)
+      {
+         a.batch0 = pl->color_begin[col]; a.nbatch_launch = pl->color_begin[col + 1] - a.batch0;
+         if (a.nbatch_launch <= 0) { continue; }
+         cudaLaunchConfig_t cfg = {};
+         cfg.gridDim = dim3((unsigned)a.nbatch_launch); cfg.blockDim = dim3(Cfg::T); cfg.dynamicSmemBytes = bytes; cfg.stream = c.stream;
+         cudaLaunchAttribute at[1];
+         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+         at[0].val.programmaticStreamSerializationAllowed = 1;
+         cfg.attrs = at; cfg.numAttrs = (col > 0 && c.tune[5] == 0) ? 1 : 0;
+         LAGB_CUDA(cudaLaunchKernelEx(&cfg, kern, tab(c), a));
+         LAGB_LAUNCH_CHECK();
+      }
+      if (WITH_DEN) { c.dt_nblocks = pl->nbatch; }
+      return LAGB_OK;
+   }
    template<int NC, bool WITH_DEN, bool FUSE>
    static int brick_launch(Ctx &c, const MassBrickIn &in, double *y)
    {
-      if constexpr (D1D == 4)   // tuning variants (lagb_tune_set key 4): elements per batch / resident CTAs
+      if (c.tune[6] == 3 || c.tune[6] == 0)
+      {
+         if constexpr (D1D == 4 && NC == 3)   // tuning variants (lagb_tune_set key 4)
+         {
+            switch (c.tune[4])
+            {
+               case 1: return brick2_launch_v<NC,WITH_DEN,FUSE,8,4,true>(c, in, y);
+               case 2: return brick2_launch_v<NC,WITH_DEN,FUSE,8,5,false>(c, in, y);
+               case 3: return brick2_launch_v<NC,WITH_DEN,FUSE,16,2,true>(c, in, y);
+               case 4: return brick2_launch_v<NC,WITH_DEN,FUSE,16,3,false>(c, in, y);
+            }
+            return brick2_launch_v<NC,WITH_DEN,FUSE,8,6,false>(c, in, y);
+         }
+         if constexpr (D1D == 4 && NC == 1)
+         {
+            switch (c.tune[4])
+            {
+               case 1: return brick2_launch_v<NC,WITH_DEN,FUSE,16,4,true>(c, in, y);
+               case 2: return brick2_launch_v<NC,WITH_DEN,FUSE,32,3,false>(c, in, y);
+               case 3: return brick2_launch_v<NC,WITH_DEN,FUSE,32,2,true>(c, in, y);
+               case 4: return brick2_launch_v<NC,WITH_DEN,FUSE,8,8,false>(c, in, y);
+            }
+            return brick2_launch_v<NC,WITH_DEN,FUSE,16,6,false>(c, in, y);
+         }
+         return brick2_launch_v<NC,WITH_DEN,FUSE,NBB,1,false>(c, in, y);
+      }
+      if constexpr (D1D == 4)   // first brick kernel: elements per batch / resident CTAs
       {
          switch (c.tune[4])
          {
             case 1: return brick_launch_v<NC,WITH_DEN,FUSE,8,3>(c, in, y);
             case 2: return brick_launch_v<NC,WITH_DEN,FUSE,16,2>(c, in, y);
-            case 3: return brick_launch_v<NC,WITH_DEN,FUSE,8,5>(c, in, y);
-            case 4: return brick_launch_v<NC,WITH_DEN,FUSE,16,1>(c, in, y);
          }
          return brick_launch_v<NC,WITH_DEN,FUSE,8,4>(c, in, y);
       }

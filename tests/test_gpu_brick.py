@@ -26,21 +26,24 @@ def test_brick_variants_vs_oracle(built, mesh, rs, ok):
     ref = np.concatenate([O.vmass_mult(x[c * P.ndofs_h1:(c + 1) * P.ndofs_h1], -1) for c in range(3)])
     for hint in (True, False):
         c = Context(P, grid_hint=hint)
-        for var in range(5):
-            c.tune(4, var)
-            for pdl_off in (0, 1):
-                c.tune(5, pdl_off)
-                y = c.empty(P.h1_vsize)
-                y.fill_(float("nan"))          # the schedule must not depend on the output's previous contents
-                c.vmass_mult_all(c.dev(x), y)
-                y2 = c.vmass_mult_all(c.dev(x)).cpu().numpy()
-                y = y.cpu().numpy()
-                assert relerr(y, ref) < 1e-12, (hint, var, pdl_off)
-                assert np.array_equal(y, y2), "brick apply must be bitwise reproducible"
-            y1 = c.vmass_mult(c.dev(x[:P.ndofs_h1]), 0).cpu().numpy()
-            r1 = ref[:P.ndofs_h1].copy(); r1[P.ess(0)] = 0.0
-            assert relerr(y1, r1) < 1e-12
-        c.tune(4, 0); c.tune(5, 0)
+        for path, shape in ((3, 0), (3, 1), (3, 2), (2, 0)):   # brick v2 with the three brick shapes, brick v1
+            c.tune(6, path)
+            c.tune(7, shape)
+            for var in range(5 if path == 3 else 3):
+                c.tune(4, var)
+                for pdl_off in (0, 1):
+                    c.tune(5, pdl_off)
+                    y = c.empty(P.h1_vsize)
+                    y.fill_(float("nan"))          # the schedule must not depend on the output's previous contents
+                    c.vmass_mult_all(c.dev(x), y)
+                    y2 = c.vmass_mult_all(c.dev(x)).cpu().numpy()
+                    y = y.cpu().numpy()
+                    assert relerr(y, ref) < 1e-12, (hint, path, shape, var, pdl_off)
+                    assert np.array_equal(y, y2), "brick apply must be bitwise reproducible"
+                y1 = c.vmass_mult(c.dev(x[:P.ndofs_h1]), 0).cpu().numpy()
+                r1 = ref[:P.ndofs_h1].copy(); r1[P.ess(0)] = 0.0
+                assert relerr(y1, r1) < 1e-12, (hint, path, shape, var)
+        c.tune(4, 0); c.tune(5, 0); c.tune(7, 0)
         c.tune(6, 1)                           # legacy atomic path still agrees
         assert relerr(c.vmass_mult_all(c.dev(x)).cpu().numpy(), ref) < 1e-12
         c.close()
@@ -57,13 +60,13 @@ def test_brick_pcg_matches_legacy_and_oracle(built, mesh, rs, ok):
     refs = [O.pcg_vmass(comp, b[comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1].copy()) for comp in range(3)]
     c = Context(P)
     sols = {}
-    for legacy in (0, 1):
+    for legacy in (3, 2, 1):                   # brick v2, brick v1, legacy atomic scatter
         c.tune(6, legacy)
         xa, its = c.pcg_vmass_all(c.dev(b), rel_tol=1e-14)
         xa2, its2 = c.pcg_vmass_all(c.dev(b), rel_tol=1e-14)
         sols[legacy] = xa.cpu().numpy()
-        if legacy == 0:
-            assert np.array_equal(sols[0], xa2.cpu().numpy()) and list(its) == list(its2), "brick PCG must be reproducible"
+        if legacy >= 2:
+            assert np.array_equal(sols[legacy], xa2.cpu().numpy()) and list(its) == list(its2), "brick PCG must be reproducible"
         for comp in range(3):
             xr, itr = refs[comp]
             assert abs(its[comp] - itr) <= 1
@@ -71,5 +74,5 @@ def test_brick_pcg_matches_legacy_and_oracle(built, mesh, rs, ok):
             assert np.all(sols[legacy][comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1][P.ess(comp)] == 0.0)
         x0, it0 = c.pcg_vmass(1, c.dev(b[P.ndofs_h1:2 * P.ndofs_h1]), rel_tol=1e-14)
         assert relerr(x0.cpu().numpy(), refs[1][0]) < 1e-11
-    assert relerr(sols[0], sols[1]) < 1e-12
+    assert relerr(sols[3], sols[1]) < 1e-12 and relerr(sols[2], sols[1]) < 1e-12
     c.close()

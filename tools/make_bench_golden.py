@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Generate tests/golden/bench_enorm.json: |e| after every RK4 step of bench.py's N=1 workloads, computed
+by the CPU oracle (test infrastructure).  bench.py compares its final |e| with the entry of the same step index
+(`parity_rel_err`).  Run on a many-core host:  python tools/make_bench_golden.py [--out path] [--steps 11]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "bench_enorm.json"))
+    ap.add_argument("--steps", type=int, default=11)
+    ap.add_argument("--cases", default="sedov_rs5,tg_rs5,sedov_rs4")
+    args = ap.parse_args()
+    import pyoracle
+    cases = {
+        "sedov_rs5": dict(mesh="cube01_hex", rs=5, problem=1, ok=3, ot=2),
+        "sedov_rs4": dict(mesh="cube01_hex", rs=4, problem=1, ok=3, ot=2),
+        "tg_rs5": dict(mesh="cube01_hex", rs=5, problem=0, ok=3, ot=2),
+        "tp_rs4_ok2": dict(mesh="box01_hex", rs=4, problem=3, ok=2, ot=1),
+        "tp_rs4_ok3": dict(mesh="box01_hex", rs=4, problem=3, ok=3, ot=2),
+    }
+    out = {}
+    if os.path.exists(args.out):
+        out = json.load(open(args.out))
+    for name in args.cases.split(","):
+        kw = cases[name]
+        t0 = time.time()
+        r = pyoracle.run(t_final=1e9, cg_tol=1e-8, max_tsteps=args.steps - 1, nthreads=os.cpu_count() or 1, **kw)
+        out[name] = {"config": kw, "cg_tol": 1e-8, "ode": "RK4", "steps_run": r["steps"],
+                     "e_norm_after_step": {str(ti): v for ti, v in r["hist"]}, "dt_last": r["dt"], "t_last": r["t"],
+                     "generated_by": "tools/make_bench_golden.py (oracle port, reference serial -pa algorithm)",
+                     "wall_s": time.time() - t0}
+        print(name, r["steps"], r["e_norm"], f"{time.time() - t0:.1f}s", flush=True)
+        json.dump(out, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--q-variants", default="0,1,2")
     ap.add_argument("--mass1-variants", default="0")
     ap.add_argument("--brick-variants", default="0,1,2,3,4")
+    ap.add_argument("--brick-shapes", default="0,1,2")
     ap.add_argument("--only", default="", help="comma list of sections: q,force,mass,l2,pcg (default all)")
     args = ap.parse_args()
     import numpy as np
@@ -89,16 +90,23 @@ def main():
                8e-9 * (dim * dim * NE * NQ + nl + dim * nd), ye)
     c.tune(1, 0)
     y1 = c.empty(nd)
-    # brick schedule (no atomics): key 4 = variant, key 5 = 1 disables programmatic dependent launch
-    for var in ([int(s) for s in args.brick_variants.split(",")] if "mass" in only else []):
-        c.tune(4, var)
-        for pdl_off in (0, 1):
-            c.tune(5, pdl_off)
-            report(f"vmass_mult_all brick variant {var} pdl {1 - pdl_off}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
-                   8e-9 * (NE * NQ + 2 * dim * nd), yv)
-        c.tune(5, 0)
-        report(f"vmass_mult (1 comp) brick variant {var}", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
-               8e-9 * (NE * NQ + 2 * nd), y1)
+    # brick schedule (no atomics): key 6 = 3 second kernel / 2 first kernel, key 7 = brick shape, key 4 = launch variant,
+    # key 5 = 1 disables programmatic dependent launch
+    for path, shape in ([(3, int(s)) for s in args.brick_shapes.split(",")] + [(2, 0)] if "mass" in only else []):
+        c.tune(6, path)
+        c.tune(7, shape)
+        for var in [int(s) for s in args.brick_variants.split(",")]:
+            if path == 2 and var > 2:
+                continue
+            c.tune(4, var)
+            for pdl_off in (0, 1):
+                c.tune(5, pdl_off)
+                report(f"vmass_mult_all brick{path - 1} shape {shape} variant {var} pdl {1 - pdl_off}",
+                       timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))), 8e-9 * (NE * NQ + 2 * dim * nd), yv)
+            c.tune(5, 0)
+            report(f"vmass_mult (1 comp) brick{path - 1} shape {shape} variant {var}",
+                   timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))), 8e-9 * (NE * NQ + 2 * nd), y1)
+    c.tune(7, 0)
     c.tune(4, 0)
     c.tune(6, 1)   # legacy atomic-scatter kernels
     for var in ([int(s) for s in args.mass1_variants.split(",")] if "mass" in only else []):
@@ -124,12 +132,12 @@ def main():
         xs.zero_()
         c.pcg_vmass_all(b, xs)
 
-    for legacy in (0, 1):
-        c.tune(6, legacy)
+    for path in (3, 2, 1):
+        c.tune(6, path)
         us = timeit(pcg, 3)
         _, its = c.pcg_vmass_all(b, c.zeros(nv))
         nit = max(its)
-        print(f"pcg_vmass_all ({'legacy' if legacy else 'brick'}): {us:.1f} us for {its} iterations -> {us / (nit + 1):.1f} us per iteration", flush=True)
+        print(f"pcg_vmass_all ({['', 'legacy', 'brick1', 'brick2'][path]}): {us:.1f} us for {its} iterations -> {us / (nit + 1):.1f} us per iteration", flush=True)
     c.tune(6, 0)
     bl = c.dev(rng.uniform(-1, 1, nl))
     us = timeit(lambda: c.cg_emass(bl), 3)
