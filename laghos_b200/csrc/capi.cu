@@ -256,7 +256,7 @@ template<typename T> static int dev_upload(T **p, const T *h, size_t n)
 
 // Brick schedule of the H1 mass apply for NB elements per batch: built on the host from the gather
 // map on first use, uploaded once (host/batch_plan.hpp).
-int get_plan(Ctx &c, int NB, const DevPlan **out)
+int get_plan(Ctx &c, int NB, DevPlan **out)
 {
    const int shape_sel = c.tune[7];
    const int key = NB | (shape_sel << 16);
@@ -312,6 +312,20 @@ int get_plan(Ctx &c, int NB, const DevPlan **out)
    rc |= dev_upload(&dp.uoff, bp.uoff.data(), bp.uoff.size());
    rc |= dev_upload(&dp.upos, bp.upos.data(), bp.upos.size());
    if (!uc.empty()) { rc |= dev_upload(&dp.ucon, uc.data(), uc.size()); }
+   if (bp.deps_ok)
+   {
+      std::vector<int> bm((size_t)bp.nbatch*4, 0);
+      for (int k = 0; k < bp.nbatch; k++)
+      {
+         int nel = 0; for (int j = 0; j < NB; j++) { nel += bp.elem[(size_t)k*NB + j] >= 0; }
+         bm[4*(size_t)k] = nel; bm[4*(size_t)k + 1] = bp.nuniq[k]; bm[4*(size_t)k + 2] = bp.tab[k];
+      }
+      rc |= dev_upload(&dp.bmeta, bm.data(), bm.size());
+      rc |= dev_upload(&dp.deps, bp.deps.data(), bp.deps.size());
+      rc |= dev_alloc(&dp.flags, (size_t)bp.nbatch);
+      rc |= dev_alloc(&dp.work_ctr, 1);
+      if (!rc) { LAGB_CUDA(cudaMemset(dp.flags, 0, sizeof(int)*(size_t)bp.nbatch)); }
+   }
    if (rc) { return LAGB_ERR_CUDA; }
    auto ins = c.plans.emplace(key, dp);
    *out = &ins.first->second;
@@ -543,6 +557,7 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    c.ndofs = d->ndofs_h1; c.ndofs_l2 = (int64_t)c.NE*c.NL;
    c.use_visc = d->use_visc; c.use_vort = d->use_vort; c.variant = d->kernel_variant; c.device = d->device;
    c.stream = (cudaStream_t)stream;
+   { cudaDeviceProp prop; LAGB_CUDA(cudaGetDeviceProperties(&prop, d->device)); c.num_sms = prop.multiProcessorCount; }
    c.ks_generic = make_generic_kernels(c.dim, c.D1D, c.Q1D);
    if (!c.ks_generic.mass_h1)
    {
@@ -610,7 +625,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (auto &kv : c.plans)
    {
       DevPlan &dp = kv.second;
-      void *pp[] = {dp.belem, dp.bnuniq, dp.btab, dp.buid, dp.lidx, dp.uoff, dp.upos, dp.ucon};
+      void *pp[] = {dp.belem, dp.bnuniq, dp.btab, dp.buid, dp.lidx, dp.uoff, dp.upos, dp.ucon, dp.bmeta, dp.deps, dp.flags, dp.work_ctr};
       for (void *p : pp) { if (p) { cudaFree(p); } }
    }
    for (auto &nb : c.nbrs) { cudaFree(nb.d_idx); cudaFree(nb.d_send); cudaFree(nb.d_recv); }

@@ -37,6 +37,8 @@ struct DevPlan
    uint16_t *lidx = nullptr, *uoff = nullptr, *upos = nullptr;
    uint16_t *ucon = nullptr;          // [ntab][UP][8] fixed-width contribution table (plane slots), nullptr if a dof has > 8
    int brick[3] = {0, 0, 0};
+   // single-launch dataflow kernel (device/mass3d_brick3.cuh)
+   int *bmeta = nullptr, *deps = nullptr, *flags = nullptr, *work_ctr = nullptr; int epoch = 0;
 };
 
 // per-(DIM,D1D,Q1D) launchers
@@ -87,6 +89,8 @@ struct Ctx
    double *d_d2 = nullptr;                                     // second search-direction buffer (fused brick PCG)
    int elem_grid[3] = {0, 0, 0};                               // structured element grid hint (0 = none)
    std::vector<int> h_map;                                     // host copy of the gather map (schedules are built lazily)
+   std::map<const void*, int> occ_cache;                       // resident CTAs per SM of the persistent kernels
+   int num_sms = 148;
    std::map<const void*, size_t> smem_optin;                   // kernels whose dynamic shared memory opt-in is set on this device
    std::map<int, DevPlan> plans;                               // brick schedules by (NB | shape key)
    double *d_lr = nullptr, *d_ld = nullptr, *d_lz = nullptr;   // [ndofs_l2]
@@ -131,7 +135,7 @@ int halo_sum(Ctx &c, double *v, int nc);              // sum shared dofs across 
 int allreduce_sum(Ctx &c, double *d_vals, int n);     // in-stream
 int allreduce_min(Ctx &c, double *d_vals, int n);
 
-int get_plan(Ctx &c, int NB, const DevPlan **out);    // brick schedule for NB elements per batch and the shape c.tune[7] (built on first use)
+int get_plan(Ctx &c, int NB, DevPlan **out);    // brick schedule for NB elements per batch and the shape c.tune[7] (built on first use)
 
 KernelSet make_generic_kernels(int dim, int D1D, int Q1D);
 bool add_tuned_kernels(KernelSet &ks, int dim, int D1D, int Q1D);

@@ -43,6 +43,9 @@ struct BatchPlan
    std::vector<uint16_t> uoff;          // [ntab*(UP+1)] CSR offsets into upos
    std::vector<uint16_t> upos;          // [ntab*NB*ND] E positions (e_loc*ND + i) sorted by unique slot
    int64_t n_first = 0;                 // number of (dof) first-writer entries == number of touched dofs
+   static constexpr int MAXDEP = 32;
+   std::vector<int> deps;               // [nbatch*MAXDEP] earlier (lower-coloured) batches sharing a dof, -1 padded
+   bool deps_ok = false;                // false: some batch has more than MAXDEP such neighbours
 
    static void brick_shape(int NB, const int grid[3], int b[3])
    {
@@ -194,6 +197,34 @@ struct BatchPlan
             upos.insert(upos.end(), up.begin(), up.end());
          }
          tab[k] = it->second;
+      }
+      // dependency lists of the single-launch dataflow kernel (device/mass3d_brick3.cuh): for the batch at
+      // schedule position k, the positions k' < k that share a dof with it (same colour never shares)
+      {
+         std::vector<int> pos(nbatch);
+         for (int k = 0; k < nbatch; k++) { pos[order[k]] = k; }
+         std::vector<int64_t> head((size_t)ndofs + 1, 0);
+         for (int b = 0; b < nbatch; b++) { for (int d : buniq[b]) { head[d + 1]++; } }
+         for (int64_t i = 0; i < ndofs; i++) { head[i + 1] += head[i]; }
+         std::vector<int> d2k((size_t)head[ndofs]);
+         std::vector<int64_t> fill(head.begin(), head.end() - 1);
+         for (int b = 0; b < nbatch; b++) { for (int d : buniq[b]) { d2k[fill[d]++] = pos[b]; } }
+         deps.assign((size_t)nbatch*MAXDEP, -1);
+         deps_ok = true;
+         std::vector<int> tmp;
+         for (int k = 0; k < nbatch; k++)
+         {
+            tmp.clear();
+            for (int d : buniq[order[k]])
+            {
+               if (head[d + 1] - head[d] < 2) { continue; }
+               for (int64_t p = head[d]; p < head[d + 1]; p++) { if (d2k[p] < k) { tmp.push_back(d2k[p]); } }
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if ((int)tmp.size() > MAXDEP) { deps_ok = false; break; }
+            for (size_t j = 0; j < tmp.size(); j++) { deps[(size_t)k*MAXDEP + j] = tmp[j]; }
+         }
       }
       return 0;
    }

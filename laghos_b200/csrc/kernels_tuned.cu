@@ -3,6 +3,7 @@
 #include <algorithm>
 #include "device/mass3d.cuh"
 #include "device/mass3d_brick.cuh"
+#include "device/mass3d_brick3.cuh"
 #include "device/staged3d.cuh"
 
 namespace lagb {
@@ -77,7 +78,7 @@ struct TunedLaunch3D
    static int brick_launch_v(Ctx &c, const MassBrickIn &in, double *y)
    {
       using Cfg = tuned::MassBrickCfg<D1D,Q1D,NB,NC>;
-      const DevPlan *pl = nullptr;
+      DevPlan *pl = nullptr;
       int rc = get_plan(c, NB, &pl); if (rc) { return rc; }
       auto kern = tuned::mass3d_brick<D1D,Q1D,NB,NC,WITH_DEN,FUSE,MINB>;
       const size_t bytes = Cfg::smem_bytes(pl->UP);
@@ -111,7 +112,7 @@ struct TunedLaunch3D
    static int brick2_launch_v(Ctx &c, const MassBrickIn &in, double *y)
    {
       using Cfg = tuned::MassBrick2Cfg<D1D,Q1D,NB,NC>;
-      const DevPlan *pl = nullptr;
+      DevPlan *pl = nullptr;
       int rc = get_plan(c, NB, &pl); if (rc) { return rc; }
       if (!pl->ucon) { set_error("mass3d_brick2: a dof has more than 8 contributions inside one batch"); return LAGB_ERR_STATE; }
       auto kern = tuned::mass3d_brick2<D1D,Q1D,NB,NC,WITH_DEN,FUSE,MINB,DBULK>;
@@ -141,9 +142,70 @@ struct TunedLaunch3D
       if (WITH_DEN) { c.dt_nblocks = pl->nbatch; }
       return LAGB_OK;
    }
+   // single-launch persistent dataflow kernel (device/mass3d_brick3.cuh); plain input only
+   template<int NC, bool WITH_DEN, int NB, int MINB, bool DBULK>
+   static int brick3_launch_v(Ctx &c, const MassBrickIn &in, double *y)
+   {
+      using Cfg = tuned::MassBrick3Cfg<D1D,Q1D,NB,NC>;
+      DevPlan *pl = nullptr;
+      int rc = get_plan(c, NB, &pl); if (rc) { return rc; }
+      if (!pl->ucon || !pl->deps) { set_error("mass3d_brick3: schedule has no fixed-width tables"); return LAGB_ERR_STATE; }
+      auto kern = tuned::mass3d_brick3<D1D,Q1D,NB,NC,WITH_DEN,MINB,DBULK>;
+      const size_t bytes = Cfg::smem_bytes(pl->UP, DBULK);
+      rc = set_smem(c, kern, bytes); if (rc) { return rc; }
+      if (WITH_DEN && pl->nbatch*NC > c.part_cap) { set_error("mass3d_brick3: partial buffer too small"); return LAGB_ERR_STATE; }
+      int &occ = c.occ_cache[(const void*)kern];
+      if (occ == 0)
+      {
+         LAGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::T, bytes));
+         if (occ < 1) { set_error("mass3d_brick3: kernel does not fit an SM"); return LAGB_ERR_STATE; }
+      }
+      tuned::Brick3Args g;
+      tuned::BrickArgs &a = g.b;
+      a.UP = pl->UP; a.NE = c.NE; a.cstride = c.ndofs; a.batch0 = 0; a.nbatch_launch = pl->nbatch;
+      a.belem = pl->belem; a.bnuniq = pl->bnuniq; a.buid = pl->buid; a.btab = pl->btab;
+      a.lidx = pl->lidx; a.uoff = pl->uoff; a.upos = pl->upos; a.ucon = pl->ucon;
+      a.Dq = c.d_massD; a.x = in.x; a.r = nullptr; a.dold = nullptr; a.dnew = nullptr;
+      a.dinv = c.d_dinv; a.ess = c.d_essmask; a.st = c.d_state; a.comp0 = in.comp0;
+      a.y = y; a.den_part = c.d_part;
+      g.nbatch_total = pl->nbatch; g.bmeta = reinterpret_cast<const int4*>(pl->bmeta); g.deps = pl->deps;
+      g.flags = pl->flags; g.work_ctr = pl->work_ctr; g.epoch = ++pl->epoch;
+      LAGB_CUDA(cudaMemsetAsync(pl->work_ctr, 0, sizeof(int), c.stream));
+      const int grid = std::min(pl->nbatch, c.num_sms*occ);
+      kern<<<grid, Cfg::T, bytes, c.stream>>>(tab(c), g);
+      LAGB_LAUNCH_CHECK();
+      if (WITH_DEN) { c.dt_nblocks = pl->nbatch; }
+      return LAGB_OK;
+   }
+   template<int NC, bool WITH_DEN>
+   static int brick3_launch(Ctx &c, const MassBrickIn &in, double *y)
+   {
+      if constexpr (D1D == 4 && NC == 3)   // tuning variants (lagb_tune_set key 4)
+      {
+         switch (c.tune[4])
+         {
+            case 1: return brick3_launch_v<NC,WITH_DEN,8,4,true>(c, in, y);
+            case 2: return brick3_launch_v<NC,WITH_DEN,8,4,false>(c, in, y);
+            case 3: return brick3_launch_v<NC,WITH_DEN,8,6,false>(c, in, y);
+            case 4: return brick3_launch_v<NC,WITH_DEN,16,2,false>(c, in, y);
+         }
+         return brick3_launch_v<NC,WITH_DEN,8,5,false>(c, in, y);
+      }
+      if constexpr (D1D == 4 && NC == 1)
+      {
+         switch (c.tune[4])
+         {
+            case 1: return brick3_launch_v<NC,WITH_DEN,16,4,true>(c, in, y);
+            case 2: return brick3_launch_v<NC,WITH_DEN,32,3,false>(c, in, y);
+         }
+         return brick3_launch_v<NC,WITH_DEN,16,6,false>(c, in, y);
+      }
+      return brick3_launch_v<NC,WITH_DEN,NBB,1,false>(c, in, y);
+   }
    template<int NC, bool WITH_DEN, bool FUSE>
    static int brick_launch(Ctx &c, const MassBrickIn &in, double *y)
    {
+      if constexpr (!FUSE) { if (c.tune[6] == 4) { return brick3_launch<NC,WITH_DEN>(c, in, y); } }
       if (c.tune[6] == 3 || c.tune[6] == 0)
       {
          if constexpr (D1D == 4 && NC == 3)   // tuning variants (lagb_tune_set key 4)

@@ -26,10 +26,10 @@ def test_brick_variants_vs_oracle(built, mesh, rs, ok):
     ref = np.concatenate([O.vmass_mult(x[c * P.ndofs_h1:(c + 1) * P.ndofs_h1], -1) for c in range(3)])
     for hint in (True, False):
         c = Context(P, grid_hint=hint)
-        for path, shape in ((3, 0), (3, 1), (3, 2), (2, 0)):   # brick v2 with the three brick shapes, brick v1
+        for path, shape in ((4, 0), (4, 1), (4, 2), (3, 0), (3, 1), (3, 2), (2, 0)):   # dataflow kernel / brick v2 with the three brick shapes, brick v1
             c.tune(6, path)
             c.tune(7, shape)
-            for var in range(5 if path == 3 else 3):
+            for var in range(5 if path >= 3 else 3):
                 c.tune(4, var)
                 for pdl_off in (0, 1):
                     c.tune(5, pdl_off)

@@ -92,14 +92,14 @@ def main():
     y1 = c.empty(nd)
     # brick schedule (no atomics): key 6 = 3 second kernel / 2 first kernel, key 7 = brick shape, key 4 = launch variant,
     # key 5 = 1 disables programmatic dependent launch
-    for path, shape in ([(3, int(s)) for s in args.brick_shapes.split(",")] + [(2, 0)] if "mass" in only else []):
+    for path, shape in ([(4, int(s)) for s in args.brick_shapes.split(",")] + [(3, int(s)) for s in args.brick_shapes.split(",")] + [(2, 0)] if "mass" in only else []):
         c.tune(6, path)
         c.tune(7, shape)
         for var in [int(s) for s in args.brick_variants.split(",")]:
             if path == 2 and var > 2:
                 continue
             c.tune(4, var)
-            for pdl_off in (0, 1):
+            for pdl_off in ((0, 1) if path < 4 else (0,)):
                 c.tune(5, pdl_off)
                 report(f"vmass_mult_all brick{path - 1} shape {shape} variant {var} pdl {1 - pdl_off}",
                        timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))), 8e-9 * (NE * NQ + 2 * dim * nd), yv)
