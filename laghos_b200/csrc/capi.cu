@@ -350,6 +350,9 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    const int g = vec_grid(n);
    if (g*NC > c.part_cap) { set_error("pcg: partial buffer too small"); return LAGB_ERR_STATE; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
+   // H1 apply through the atomic-free brick kernels (plain stores): no zero fill of z anywhere
+   const bool bapply = !l2 && c.variant == 0 && ks.mass_brick != nullptr && c.tune[6] >= 2 && (NC == 1 || NC == 3);
+   const bool zero_z = !l2 && !bapply;   // only the atomic scatter accumulates into z
 
    // apply: z (+)= A v ; returns number of partial blocks if the kernel produced d^t A d partials
    auto apply = [&](const double *v, bool want_den, int &den_blocks) -> int
@@ -357,10 +360,12 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       den_blocks = 0;
       if (l2) { return ks.mass_l2(c, v, z); }
       if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
-      int rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass);
+      int rc;
+      if (bapply) { MassBrickIn in; in.x = v; rc = ks.mass_brick(c, NC, in, z, want_den); }
+      else { rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass); }
       if (rc) { return rc; }
       if (c.profile_mass) { int rt = timer_end(c, 4); if (rt) { return rt; } c.mass_launches++; }
-      if (want_den && ks.tuned_mass) { den_blocks = c.dt_nblocks; }
+      if (want_den && (ks.tuned_mass || bapply)) { den_blocks = c.dt_nblocks; }
       return halo_sum(c, z, NC);
    };
    // per-block partials -> (sum over ranks) -> what the finish kernels read.
@@ -380,7 +385,7 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    const double *src = nullptr;
    if (iterative_mode)
    {
-      if (!l2) { LAGB_CUDA(cudaMemsetAsync(z, 0, sizeof(double)*NC*n, c.stream)); }
+      if (zero_z) { LAGB_CUDA(cudaMemsetAsync(z, 0, sizeof(double)*NC*n, c.stream)); }
       rc = apply(x, false, den_blocks); if (rc) { return rc; }
    }
    else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
@@ -417,13 +422,29 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       rc = reduced(den_blocks, c.d_tmp, src, nsrc); if (rc) { return rc; }
       pcg::finish_den<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it);
       LAGB_LAUNCH_CHECK();
-      pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, d, z, P, own, c.d_part);
-      LAGB_LAUNCH_CHECK();
-      rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
-      pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
-      LAGB_LAUNCH_CHECK();
-      pcg::update_d<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, d, r, P, z);
-      LAGB_LAUNCH_CHECK();
+      if (c.tune[8] == 1)
+      {
+         // first version: x and r in one kernel, d (and the zero fill of z) in another
+         pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, d, z, P, own, c.d_part);
+         LAGB_LAUNCH_CHECK();
+         rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
+         pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
+         LAGB_LAUNCH_CHECK();
+         pcg::update_d<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, d, r, P, z);
+         LAGB_LAUNCH_CHECK();
+      }
+      else
+      {
+         // same arithmetic, one vector pass less: x is updated where d is read anyway
+         pcg::update_r<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, r, z, P, own, c.d_part);
+         LAGB_LAUNCH_CHECK();
+         rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
+         pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
+         LAGB_LAUNCH_CHECK();
+         if (zero_z) { pcg::update_dx<NC,true><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, d, r, P, z); }
+         else { pcg::update_dx<NC,false><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, d, r, P, z); }
+         LAGB_LAUNCH_CHECK();
+      }
       if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
    }
    if (!finished) { rc = poll(); if (rc) { return rc; } }
@@ -517,7 +538,7 @@ static bool use_brick(const Ctx &c) { return c.variant == 0 && c.ks.mass_brick !
 static int pcg_run(Ctx &c, bool l2, int nc, int comp0, const double *b, double *x, double rel_tol,
                    int max_iter, bool iterative_mode, int *h_iters)
 {
-   if (!l2 && use_brick(c))
+   if (!l2 && use_brick(c) && c.tune[6] <= 3 && c.tune[9] == 0)   // fused direction update (multi-launch brick kernels)
    {
       if (nc == 1) { return pcg_run_brick<1>(c, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters); }
       if (nc == 3) { return pcg_run_brick<3>(c, comp0, b, x, rel_tol, max_iter, iterative_mode, h_iters); }

@@ -107,7 +107,8 @@ struct Ctx
    int dt_nblocks = 0;
    // lagb_tune_set: [0] legacy mass3d NC=3 variant, [1] force, [2] qupdate, [3] legacy mass3d NC=1, [4] brick launch
    // variant, [5] 1 = no programmatic dependent launch, [6] mass path (0 default, 1 legacy atomic, 2 brick v1, 3 brick v2),
-   // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil)
+   // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil), [8] 1 = first PCG vector kernels (update_xr/update_d),
+   // [9] 1 = plain (not fused) PCG on the multi-launch brick kernels
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing

@@ -128,24 +128,36 @@ __global__ void reduce_partials(int nblocks, const double *__restrict__ part, do
 }
 
 // Fixed-order reduction of part[b*NC + c], b < nblocks, by one block of FB threads: thread t
-// sums b = t, t+FB, ... (4 independent partial sums keep the loads in flight), then a
+// sums b = t, t+FB, ... with 8 independent partial sums per component and all components in one
+// sweep (up to 24 loads in flight per thread: the kernel is pure load latency), then a
 // shuffle/shared tree.  Result valid on thread 0.
 constexpr int FB = 1024;
 template<int NC>
 __device__ __forceinline__ void reduce_to_thread0(const double *__restrict__ part, int nblocks, double *out, double *sh)
 {
+   constexpr int W = 8;
+   double a[NC][W];
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int w = 0; w < W; w++) { a[c][w] = 0.0; }
+   int b = threadIdx.x;
+   for (; b + (W - 1)*FB < nblocks; b += W*FB)
+   {
+#pragma unroll
+      for (int w = 0; w < W; w++)
+#pragma unroll
+         for (int c = 0; c < NC; c++) { a[c][w] += part[(size_t)(b + w*FB)*NC + c]; }
+   }
+   for (; b < nblocks; b += FB)
+   {
+#pragma unroll
+      for (int c = 0; c < NC; c++) { a[c][0] += part[(size_t)b*NC + c]; }
+   }
 #pragma unroll
    for (int c = 0; c < NC; c++)
    {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int b = threadIdx.x;
-      for (; b + 3*FB < nblocks; b += 4*FB)
-      {
-         a0 += part[(size_t)b*NC + c]; a1 += part[(size_t)(b + FB)*NC + c];
-         a2 += part[(size_t)(b + 2*FB)*NC + c]; a3 += part[(size_t)(b + 3*FB)*NC + c];
-      }
-      for (; b < nblocks; b += FB) { a0 += part[(size_t)b*NC + c]; }
-      out[c] = block_sum((a0 + a1) + (a2 + a3), sh);
+      out[c] = block_sum(((a[c][0] + a[c][1]) + (a[c][2] + a[c][3])) + ((a[c][4] + a[c][5]) + (a[c][6] + a[c][7])), sh);
    }
 }
 
@@ -195,7 +207,7 @@ __global__ void finish_den(State *st, const double *part, int nblocks, int iter)
    if (threadIdx.x != 0) { return; }
    for (int c = 0; c < NC; c++)
    {
-      if (st->done[c]) { continue; }
+      if (st->done[c]) { st->alpha[c] = 0.0; continue; }   // stopped earlier: the x update below runs with alpha = 0
       const double den = tmp[c];
       st->den[c] = den;
       if (den == 0.0)
@@ -343,6 +355,117 @@ update_d(int64_t n, int64_t cstride, const State *__restrict__ st,
                const double zz = ((em[u] >> c) & 1u) ? 0.0 : di[u]*rv[u][c];
                d[k] = skip[c] ? dv[u][c] : zz + beta[c]*dv[u][c];
                z[k] = 0.0;
+            }
+         }
+      }
+   }
+}
+
+// Two-kernel split of the same arithmetic with one vector pass less per iteration: the x update
+// moves from the residual kernel to the direction kernel, which reads d anyway.
+//   update_r : r -= alpha z ; betanom_part = sum own*r*(M^-1 r)            (reads r, z; writes r)
+//   update_dx: x += alpha d ; d = M^-1 r + beta d ; [z = 0]                (reads x, d, r; writes x, d)
+// alpha of a component that stopped in an EARLIER iteration is 0 (finish_den), a component that
+// converged in THIS iteration still gets its x update (MFEM updates x before the convergence test).
+template<int NC>
+__global__ void __launch_bounds__(RB)
+update_r(int64_t n, int64_t cstride, const State *__restrict__ st,
+         double *__restrict__ r, const double *__restrict__ z, const Prec P,
+         const unsigned char *__restrict__ own, double *__restrict__ part)
+{
+   constexpr int UNR = 4;
+   __shared__ double sh[32];
+   double acc[NC], alpha[NC];
+#pragma unroll
+   for (int c = 0; c < NC; c++) { acc[c] = 0.0; alpha[c] = st->done[c] ? 0.0 : st->alpha[c]; }
+   const int64_t stride = (int64_t)gridDim.x*blockDim.x;
+   for (int64_t i0 = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += UNR*stride)
+   {
+      double rv[UNR][NC], zv[UNR][NC], di[UNR], w[UNR];
+      unsigned int em[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+      {
+         const int64_t i = i0 + u*stride;
+         const bool ok = i < n;
+         di[u] = (ok && P.dinv) ? P.dinv[i] : 1.0;
+         em[u] = (ok && P.ess) ? (unsigned int)P.ess[i] >> P.comp0 : 0u;
+         w[u] = (ok && own) ? (double)own[i] : 1.0;
+#pragma unroll
+         for (int c = 0; c < NC; c++)
+         {
+            const int64_t k = i + c*cstride;
+            rv[u][c] = ok ? r[k] : 0.0; zv[u][c] = ok ? z[k] : 0.0;
+         }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+      {
+         const int64_t i = i0 + u*stride;
+         if (i < n)
+         {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+            {
+               const double rr = rv[u][c] - alpha[c]*zv[u][c];
+               r[i + c*cstride] = rr;
+               const double zz = ((em[u] >> c) & 1u) ? 0.0 : di[u]*rr;
+               acc[c] += w[u]*rr*zz;
+            }
+         }
+      }
+   }
+#pragma unroll
+   for (int c = 0; c < NC; c++)
+   {
+      const double s = block_sum(acc[c], sh);
+      if (threadIdx.x == 0) { part[(size_t)blockIdx.x*NC + c] = s; }
+   }
+}
+
+template<int NC, bool ZERO_Z>
+__global__ void __launch_bounds__(RB)
+update_dx(int64_t n, int64_t cstride, const State *__restrict__ st,
+          double *__restrict__ x, double *__restrict__ d, const double *__restrict__ r,
+          const Prec P, double *__restrict__ z)
+{
+   constexpr int UNR = 2;
+   double alpha[NC], beta[NC]; bool skip[NC];
+#pragma unroll
+   for (int c = 0; c < NC; c++) { alpha[c] = st->alpha[c]; beta[c] = st->beta[c]; skip[c] = st->done[c] != 0; }
+   const int64_t stride = (int64_t)gridDim.x*blockDim.x;
+   for (int64_t i0 = blockIdx.x*(int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += UNR*stride)
+   {
+      double xv[UNR][NC], dv[UNR][NC], rv[UNR][NC], di[UNR];
+      unsigned int em[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+      {
+         const int64_t i = i0 + u*stride;
+         const bool ok = i < n;
+         di[u] = (ok && P.dinv) ? P.dinv[i] : 1.0;
+         em[u] = (ok && P.ess) ? (unsigned int)P.ess[i] >> P.comp0 : 0u;
+#pragma unroll
+         for (int c = 0; c < NC; c++)
+         {
+            const int64_t k = i + c*cstride;
+            xv[u][c] = ok ? x[k] : 0.0; dv[u][c] = ok ? d[k] : 0.0; rv[u][c] = ok ? r[k] : 0.0;
+         }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+      {
+         const int64_t i = i0 + u*stride;
+         if (i < n)
+         {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+            {
+               const int64_t k = i + c*cstride;
+               x[k] = xv[u][c] + alpha[c]*dv[u][c];
+               const double zz = ((em[u] >> c) & 1u) ? 0.0 : di[u]*rv[u][c];
+               d[k] = skip[c] ? dv[u][c] : zz + beta[c]*dv[u][c];
+               if (ZERO_Z) { z[k] = 0.0; }
             }
          }
       }

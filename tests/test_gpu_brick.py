@@ -60,7 +60,7 @@ def test_brick_pcg_matches_legacy_and_oracle(built, mesh, rs, ok):
     refs = [O.pcg_vmass(comp, b[comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1].copy()) for comp in range(3)]
     c = Context(P)
     sols = {}
-    for legacy in (3, 2, 1):                   # brick v2, brick v1, legacy atomic scatter
+    for legacy in (4, 3, 2, 1):                # dataflow kernel (plain PCG), brick v2 / v1 (fused PCG), legacy atomic scatter
         c.tune(6, legacy)
         xa, its = c.pcg_vmass_all(c.dev(b), rel_tol=1e-14)
         xa2, its2 = c.pcg_vmass_all(c.dev(b), rel_tol=1e-14)
@@ -74,5 +74,15 @@ def test_brick_pcg_matches_legacy_and_oracle(built, mesh, rs, ok):
             assert np.all(sols[legacy][comp * P.ndofs_h1:(comp + 1) * P.ndofs_h1][P.ess(comp)] == 0.0)
         x0, it0 = c.pcg_vmass(1, c.dev(b[P.ndofs_h1:2 * P.ndofs_h1]), rel_tol=1e-14)
         assert relerr(x0.cpu().numpy(), refs[1][0]) < 1e-11
-    assert relerr(sols[3], sols[1]) < 1e-12 and relerr(sols[2], sols[1]) < 1e-12
+    assert relerr(sols[3], sols[1]) < 1e-12 and relerr(sols[2], sols[1]) < 1e-12 and relerr(sols[4], sols[1]) < 1e-12
+    # the split vector kernels (x updated in the direction kernel) reproduce the first version bit for bit
+    c.tune(6, 4)
+    c.tune(8, 1)
+    xo, ito = c.pcg_vmass_all(c.dev(b), rel_tol=1e-14)
+    assert np.array_equal(xo.cpu().numpy(), sols[4]) and list(ito) == list(its)
+    c.tune(8, 0)
+    c.tune(9, 1)                               # plain PCG on the multi-launch brick kernel
+    c.tune(6, 3)
+    xp, itp = c.pcg_vmass_all(c.dev(b), rel_tol=1e-14)
+    assert relerr(xp.cpu().numpy(), sols[1]) < 1e-12
     c.close()
