@@ -7,7 +7,7 @@ ARCH = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -diag-suppress 128
 CXXFLAGS = -O2 -std=c++17 -fPIC -Wall
 CS = laghos_b200/csrc
-OBJ = build/capi.o build/kernels_generic.o build/kernels_tuned.o build/problem_capi.o build/laghos_shim.o
+OBJ = build/capi.o build/kernels_generic.o build/kernels_tuned.o build/kernels_l2.o build/problem_capi.o build/laghos_shim.o
 DEV_HDRS = $(wildcard $(CS)/device/*.cuh) $(CS)/ctx.hpp include/laghos_b200.h
 HOST_HDRS = $(wildcard $(CS)/host/*.hpp) include/laghos_b200.h
 

@@ -9,6 +9,8 @@ Force^T, CG(L2 mass)] + the post-step dt estimate) through the restated driver l
 (lagb_laghos_run = reference laghos.cpp:742-778) on the 3D Sedov problem, Q3/Q2.
 
 N = 1 : BASELINE config[1]  cube01_hex -p 1 -rs 5 -ok 3 -ot 2 -pa  (64^3 elements).
+        --problem 0 : BASELINE config[2] (3D Taylor-Green, same mesh and orders);
+        --workload box01 --ok {2,3,4,5} : BASELINE config[4] (triple point, box01_hex -rs 4, order sweep).
 N > 1 : weak scaling, one 64^3-element block per GPU (2x1x1, 2x2x1, 2x2x2 blocks; N = 8 is
         BASELINE config[3], cube01_hex -rs 6), launched by torchrun, NCCL for the CG dots,
         the shared-dof sums and min(dt).
@@ -36,17 +38,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mdof x steps / s (major kernels total rate), 3D Sedov Q3/Q2 -pa"
+PROBLEM_NAMES = {0: "Taylor-Green", 1: "Sedov", 3: "triple-point"}
+COARSE = {"cube01": (2, 2, 2), "box01": (4, 2, 2)}     # elements per axis of the reference data/ meshes
 UNIT = "Mdof*steps/s"
 PGRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def workload(n_gpus, rs):
+def workload(n_gpus, rs, name="cube01", problem=1, ok=3):
     """mesh name + rs such that every GPU owns a (2^rs)^3-element block of edge-2^-(rs+1) hexes."""
     pg = PGRIDS[n_gpus]
+    tail = f"-p {problem} -rs {{}} -ok {ok} -ot {ok - 1} -pa"
+    if name == "box01":
+        if n_gpus != 1:
+            raise SystemExit("--workload box01 (BASELINE config 5) is a 1-GPU configuration")
+        return dict(mesh="box01_hex", rs=rs), pg, "box01_hex " + tail.format(rs)
     if n_gpus == 1:
-        return dict(mesh="cube01_hex", rs=rs), pg, f"cube01_hex -p 1 -rs {rs} -ok 3 -ot 2 -pa"
+        return dict(mesh="cube01_hex", rs=rs), pg, "cube01_hex " + tail.format(rs)
     mesh = "cube01_hex" if n_gpus == 8 else f"hexbox_{pg[0]}x{pg[1]}x{pg[2]}"
-    return dict(mesh=mesh, rs=rs + 1), pg, f"{mesh} -p 1 -rs {rs + 1} -ok 3 -ot 2 -pa, {pg[0]}x{pg[1]}x{pg[2]} blocks"
+    return dict(mesh=mesh, rs=rs + 1), pg, f"{mesh} " + tail.format(rs + 1) + f", {pg[0]}x{pg[1]}x{pg[2]} blocks"
+
+
+def golden_e_norm(name, problem, rs, ok, step):
+    """|e| of the CPU oracle after `step` RK4 steps of this workload (tests/golden/bench_enorm.json, written
+    by tools/make_bench_golden.py), or None if that configuration / step was not generated."""
+    p = os.path.join(ROOT, "tests", "golden", "bench_enorm.json")
+    if not os.path.exists(p):
+        return None
+    key = {("cube01", 1, 3): f"sedov_rs{rs}", ("cube01", 0, 3): f"tg_rs{rs}",
+           ("box01", 3, 2): f"tp_rs{rs}_ok2", ("box01", 3, 3): f"tp_rs{rs}_ok3"}.get((name, problem, ok))
+    ent = json.load(open(p)).get(key) if key else None
+    if not ent:
+        return None
+    return ent["e_norm_after_step"].get(str(step))
 
 
 class ClockSampler:
@@ -103,49 +126,46 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_oracle_run(threads, budget_s, steps, warmup):
-    """The reference's CPU -pa algorithm (oracle port, element-parallel over `threads` host threads,
-    the stand-in for `mpirun -np <cores> laghos`) on a bounded sample of the same workload:
-    same problem / orders, smaller -rs.  Returns (rate, sample description, work, seconds)."""
+REF_RS = 4   # the CPU arm always runs cube01_hex -p 1 -rs 4 -ok 3 -ot 2 (32^3 elements): one fixed configuration
+
+
+def cpu_oracle_run(threads, steps, rs=REF_RS, warm=True):
+    """The reference's CPU -pa algorithm (oracle port, element-parallel over `threads` host threads, the
+    stand-in for `mpirun -np <cores> laghos`) on a FIXED sample of the same workload: same problem and
+    orders at -rs `rs`, `steps` RK4 steps from t = 0 after a discarded 2-step warm-up run (thread start-up,
+    page faults).  Rates are per dof, so they compare across -rs.  Returns (rate, sample, seconds, result)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
-    kw = dict(mesh="cube01_hex", problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, nthreads=threads)
-    rs, best = 3, None
-    t_total0 = time.time()
-    while rs <= 5:
-        t0 = time.time()
-        kw["nthreads"] = max(1, min(threads, (2 ** (rs + 1)) ** 3 // 64))
-        r = pyoracle.run(rs=rs, max_tsteps=steps + warmup - 1, **kw)
-        el = time.time() - t0
-        best = (rs, r, el)
-        # next level costs ~8x; stop when it would not fit the budget
-        if (time.time() - t_total0) + 8.5 * el > budget_s:
-            break
-        rs += 1
-    rs, r, el = best
-    T = r["t_cgH1"] + r["t_force"] + r["t_qdata"]
-    threads = kw["nthreads"]
+    kw = dict(mesh="cube01_hex", problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, nthreads=threads, rs=rs)
+    if warm:
+        pyoracle.run(max_tsteps=1, **kw)
+    t0 = time.time()
+    r = pyoracle.run(max_tsteps=steps - 1, **kw)
+    el = time.time() - t0
     sample = (f"oracle port (reference serial -pa algorithm, {threads} element-parallel host threads), "
               f"cube01_hex -p 1 -rs {rs} -ok 3 -ot 2, {r['steps']} RK4 steps from t=0, {el:.1f} s wall")
-    return r["fom"][0], sample, T, el, rs, r, threads
+    return r["fom"][0], sample, el, r
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the
-    reference binary cannot be built here: MFEM/MPI/hypre absent)."""
+    reference binary cannot be built here: MFEM/MPI/hypre absent).  Fixed configuration
+    (-rs 4, all host threads, --steps steps after a 2-step warm-up run) so that two boxes with the same
+    core count report the same number."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    fom, sample, T, el, rs, r, threads = cpu_oracle_run(threads, budget_s=150.0, steps=args.steps, warmup=0)
-    steps = max(r["steps"], 1)
+    steps = max(args.steps, 1)
+    fom, sample, el, r = cpu_oracle_run(threads, steps)
+    T = r["t_cgH1"] + r["t_force"] + r["t_qdata"]
     work = fom * T
     line = {
         "impl": "reference", "metric": METRIC, "value": fom, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": 0, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+        "steps": r["steps"], "warmup": 2, "ms_per_step": 1e3 * el / max(r["steps"], 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3D Sedov cube01_hex -p 1 -ok 3 -ot 2 -pa, bounded CPU sample -rs {rs} "
-                               f"(GPU arm runs -rs {args.rs}); rates are per dof so they compare",
-                   "cg_tol": 1e-8, "ode": "RK4"},
+        "config": {"workload": f"cube01_hex -p 1 -rs {REF_RS} -ok 3 -ot 2 -pa (fixed CPU sample of the GPU arm's "
+                               f"-rs {args.rs} workload; rates are per dof so they compare)",
+                   "cg_tol": 1e-8, "ode": "RK4", "host_threads": threads},
         "cpu_baseline": {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": work / el, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -159,11 +179,18 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--rs", type=int, default=5, help="refinements per GPU block (5 = 64^3 elements, BASELINE)")
+    ap.add_argument("--rs", type=int, default=None, help="refinements per GPU block (default 5 = 64^3 elements for cube01, 4 for box01: BASELINE)")
+    ap.add_argument("--workload", default="cube01", choices=["cube01", "box01"])
+    ap.add_argument("--problem", type=int, default=None, help="1 Sedov (default), 0 Taylor-Green, 3 triple point (box01 default)")
+    ap.add_argument("--ok", type=int, default=3, help="kinematic order (thermodynamic order = ok - 1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     args = ap.parse_args()
+    if args.rs is None:
+        args.rs = 5 if args.workload == "cube01" else 4
+    if args.problem is None:
+        args.problem = 1 if args.workload == "cube01" else 3
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -201,8 +228,8 @@ def main():
         dist.broadcast(idt, 0)
         return bytes(idt.cpu().tolist())
 
-    wl, pg, wl_name = workload(args.gpus, args.rs)
-    kw = dict(problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, max_tsteps=args.warmup + args.steps - 1,   # the reference loop runs max_tsteps + 1 steps (laghos.cpp:749-760)
+    wl, pg, wl_name = workload(args.gpus, args.rs, args.workload, args.problem, args.ok)
+    kw = dict(problem=args.problem, ok=args.ok, ot=args.ok - 1, t_final=1e9, cg_tol=1e-8, max_tsteps=args.warmup + args.steps - 1,   # the reference loop runs max_tsteps + 1 steps (laghos.cpp:749-760)
               warmup_steps=args.warmup, kernel_variant=args.variant, device=local, rank=rank, nranks=world,
               pgrid=pg, **wl)
 
@@ -241,8 +268,10 @@ def main():
     if rank == 0:
         timed_steps = r["steps"] - args.warmup
         peak, peak_src = peaks()
-        n1 = 2 ** (args.rs + 1)          # elements per axis of one GPU's block (cube01_hex: 2 coarse cells x 2^rs)
-        NE_loc, NQ, nd_loc = n1 ** 3, 216, (3 * n1 + 1) ** 3
+        # elements per axis of one GPU's block (coarse cells x 2^rs), quadrature points and H1 dofs of the block
+        nel = [cx * 2 ** args.rs for cx in COARSE[args.workload]]
+        NE_loc, NQ = nel[0] * nel[1] * nel[2], (2 * args.ok) ** 3
+        nd_loc = (args.ok * nel[0] + 1) * (args.ok * nel[1] + 1) * (args.ok * nel[2] + 1)
         ncomp = int(r["mass_kernel_ncomp"])
         alg_bytes = 8.0 * (NQ * NE_loc + 2 * ncomp * nd_loc)
         nl = max(int(r["mass_kernel_launches"]), 1)
@@ -253,8 +282,11 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         T_major = r["fom"][4]
+        metric = METRIC if (args.problem, args.ok) == (1, 3) else \
+            f"Mdof x steps / s (major kernels total rate), 3D {PROBLEM_NAMES.get(args.problem, args.problem)} Q{args.ok}/Q{args.ok - 1} -pa"
+        gold = golden_e_norm(args.workload, args.problem, args.rs, args.ok, r["steps"]) if args.gpus == 1 else None
         line = {
-            "metric": METRIC, "value": r["fom"][0], "unit": UNIT, "n_gpus": args.gpus, "steps": timed_steps,
+            "metric": metric, "value": r["fom"][0], "unit": UNIT, "n_gpus": args.gpus, "steps": timed_steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * loop_s / max(timed_steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "elements_per_gpu": NE_loc, "h1_dofs_global": r["ndofs_h1_global"],
@@ -265,18 +297,27 @@ def main():
                        "qdata_Mquad_steps_per_s": r["fom"][3], "t_cgH1_s": r["t_cgH1"], "t_force_s": r["t_force"],
                        "t_qdata_s": r["t_qdata"], "t_cgL2_s": r["t_cgL2"], "t_major_s": T_major,
                        "H1_cg_iterations": r["H1iter"], "loop_device_s": loop_s},
-            "roofline": {"kernel": f"mass3d<4,6> NC={ncomp} (H1 mass PA apply inside the batched PCG)",
+            "roofline": {"kernel": f"mass3d<{args.ok + 1},{2 * args.ok}> NC={ncomp} (H1 mass PA apply inside the batched PCG)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e6 * avg_s, "launches": nl,
                          "share_of_major_time": r["mass_kernel_seconds"] / T_major if T_major > 0 else None},
             "e2e": e2e, "gpu_launches": int(r["kernel_launches"]), "clocks": clocks,
             "e_norm": r["e_norm"],
+            # |e| after the same number of steps by the CPU oracle (tests/golden/bench_enorm.json); north_star bar 1e-9
+            "parity_rel_err": (abs(r["e_norm"] - gold) / abs(gold)) if gold else None,
+            "parity_ref": {"e_norm": gold, "step": r["steps"], "source": "tests/golden/bench_enorm.json (CPU oracle)"} if gold else None,
         }
+        if traffic is not None and args.ok != 3:
+            line["roofline"]["traffic"] = None          # the committed ncu capture is of the Q3Q2 kernel
         if not args.no_cpu and args.gpus == 1:
             threads = os.cpu_count() or 1
-            fom, sample, _, _, _, _, threads = cpu_oracle_run(threads, budget_s=25.0, steps=2, warmup=0)
+            fom, sample, el4, _ = cpu_oracle_run(threads, steps=2, warm=False)
             line["cpu_baseline"] = {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+            if el4 < 6.0:
+                # one more leg on the BASELINE size itself (-rs 5) when the host has the cores for it (~8x the work)
+                fom5, sample5, _, _ = cpu_oracle_run(threads, steps=1, rs=5, warm=False)
+                line["cpu_baseline"]["rs5"] = {"value": fom5, "sample": sample5}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

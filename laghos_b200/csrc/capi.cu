@@ -641,7 +641,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    cudaStreamSynchronize(c.stream);
    void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_inv_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
                    c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinv, c.d_essmask, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
-                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own, c.d_d2};
+                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own, c.d_d2, c.d_l2inv, c.d_BL};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
    for (auto &kv : c.plans)
    {
@@ -873,11 +873,18 @@ int lagb_cg_emass(lagb_ctx *h, const double *d_b, double *d_x, double rel_tol, i
    if (!c.setup_done) { set_error("cg_emass: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    int rc = timer_begin(c, 1); if (rc) { return rc; }
    int it = 0;
-   const int pred = c.predicted_iters;
-   c.predicted_iters = 0;
-   rc = pcg_run(c, true, 1, 0, d_b, d_x, rel_tol, max_iter, false, &it);
-   c.predicted_iters = pred;
-   if (rc) { return rc; }
+   // element inverses unless the CG is asked for (lagb_tune_set key 10 / LAGB_L2_SOLVER=cg):
+   // reported as 0 iterations, which the reference counts as one (laghos_solver.cpp:485-486)
+   bool direct = false;
+   rc = l2_direct_solve(c, d_b, d_x, &direct); if (rc) { return rc; }
+   if (!direct)
+   {
+      const int pred = c.predicted_iters;
+      c.predicted_iters = 0;
+      rc = pcg_run(c, true, 1, 0, d_b, d_x, rel_tol, max_iter, false, &it);
+      c.predicted_iters = pred;
+      if (rc) { return rc; }
+   }
    rc = timer_end(c, 1); if (rc) { return rc; }
    c.L2iter += (it == 0) ? 1 : it;   // reference laghos_solver.cpp:485-486
    if (iters) { *iters = it; }

@@ -94,6 +94,8 @@ struct Ctx
    std::map<const void*, size_t> smem_optin;                   // kernels whose dynamic shared memory opt-in is set on this device
    std::map<int, DevPlan> plans;                               // brick schedules by (NB | shape key)
    double *d_lr = nullptr, *d_ld = nullptr, *d_lz = nullptr;   // [ndofs_l2]
+   // element inverses of the L2 mass matrix (device/l2solve.cuh), built on the first energy solve
+   double *d_l2inv = nullptr, *d_BL = nullptr; int l2inv_state = 0;   // 0 not tried, 1 ready, -1 unavailable (memory)
    double *d_part = nullptr; int part_cap = 0;                 // reduction partials
    double *d_tmp = nullptr;                                    // [8] reduced scalars
    double *d_dt = nullptr;                                     // [1]
@@ -108,7 +110,8 @@ struct Ctx
    // lagb_tune_set: [0] legacy mass3d NC=3 variant, [1] force, [2] qupdate, [3] legacy mass3d NC=1, [4] brick launch
    // variant, [5] 1 = no programmatic dependent launch, [6] mass path (0 default, 1 legacy atomic, 2 brick v1, 3 brick v2),
    // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil), [8] 1 = first PCG vector kernels (update_xr/update_d),
-   // [9] 1 = plain (not fused) PCG on the multi-launch brick kernels
+   // [9] 1 = plain (not fused) PCG on the multi-launch brick kernels, [10] 1 = energy solve by the reference's CG
+   // instead of the element inverses
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing
@@ -136,6 +139,7 @@ int halo_sum(Ctx &c, double *v, int nc);              // sum shared dofs across 
 int allreduce_sum(Ctx &c, double *d_vals, int n);     // in-stream
 int allreduce_min(Ctx &c, double *d_vals, int n);
 
+int l2_direct_solve(Ctx &c, const double *b, double *x, bool *done);   // kernels_l2.cu; *done = false: not available
 int get_plan(Ctx &c, int NB, DevPlan **out);    // brick schedule for NB elements per batch and the shape c.tune[7] (built on first use)
 
 KernelSet make_generic_kernels(int dim, int D1D, int Q1D);

@@ -60,9 +60,11 @@ struct QPointParams
 };
 
 // Per-point physics of reference QUpdateBody<DIM> (laghos_solver.cpp:1042-1168).
-// J, dV column-major [c + DIM*d]; J0inv as stored in QuadratureData::Jac0inv.
+// J, dV column-major [c + DIM*d]; J0inv as stored in QuadratureData::Jac0inv (read where it is used,
+// from shared or global memory: nothing of it is held in registers across the eigen-solve).
 // Writes sJ[vd + gd*DIM] = (stress J^-T)(vd,gd) * w * detJ and returns the point's
 // dt estimate (already min'ed with p.dt_in).
+// Divisions and square roots go through qm::frcp / fdiv / fsqrt (<= 1 ulp, no slow-path calls).
 template<int DIM>
 __device__ __forceinline__ double qpoint(const double *J, const double *dV, const double e_q,
                                          const double rho0DetJ0w, const double *J0inv,
@@ -72,31 +74,29 @@ __device__ __forceinline__ double qpoint(const double *J, const double *dV, cons
    constexpr int DIM2 = DIM*DIM;
    double Jinv[DIM2], stress[DIM2];
    double detJ;
+   if (DIM == 2) { detJ = J[0]*J[3] - J[1]*J[2]; }
+   else { detJ = J[0]*(J[4]*J[8] - J[5]*J[7]) + J[3]*(J[2]*J[7] - J[1]*J[8]) + J[6]*(J[1]*J[5] - J[2]*J[4]); }
+   const double idetJ = qm::frcp(detJ);
    if (DIM == 2)
    {
-      detJ = J[0]*J[3] - J[1]*J[2];
-      const double t = 1.0/detJ;
-      Jinv[0] =  J[3]*t; Jinv[1] = -J[1]*t; Jinv[2] = -J[2]*t; Jinv[3] = J[0]*t;
+      Jinv[0] =  J[3]*idetJ; Jinv[1] = -J[1]*idetJ; Jinv[2] = -J[2]*idetJ; Jinv[3] = J[0]*idetJ;
    }
    else
    {
-      detJ = J[0]*(J[4]*J[8] - J[5]*J[7]) + J[3]*(J[2]*J[7] - J[1]*J[8]) + J[6]*(J[1]*J[5] - J[2]*J[4]);
-      const double t = 1.0/detJ;
-      Jinv[0] = (J[4]*J[8] - J[5]*J[7])*t;
-      Jinv[1] = (J[7]*J[2] - J[8]*J[1])*t;
-      Jinv[2] = (J[1]*J[5] - J[2]*J[4])*t;
-      Jinv[3] = (J[5]*J[6] - J[3]*J[8])*t;
-      Jinv[4] = (J[8]*J[0] - J[6]*J[2])*t;
-      Jinv[5] = (J[2]*J[3] - J[0]*J[5])*t;
-      Jinv[6] = (J[3]*J[7] - J[4]*J[6])*t;
-      Jinv[7] = (J[6]*J[1] - J[7]*J[0])*t;
-      Jinv[8] = (J[0]*J[4] - J[1]*J[3])*t;
+      Jinv[0] = (J[4]*J[8] - J[5]*J[7])*idetJ;
+      Jinv[1] = (J[7]*J[2] - J[8]*J[1])*idetJ;
+      Jinv[2] = (J[1]*J[5] - J[2]*J[4])*idetJ;
+      Jinv[3] = (J[5]*J[6] - J[3]*J[8])*idetJ;
+      Jinv[4] = (J[8]*J[0] - J[6]*J[2])*idetJ;
+      Jinv[5] = (J[2]*J[3] - J[0]*J[5])*idetJ;
+      Jinv[6] = (J[3]*J[7] - J[4]*J[6])*idetJ;
+      Jinv[7] = (J[6]*J[1] - J[7]*J[0])*idetJ;
+      Jinv[8] = (J[0]*J[4] - J[1]*J[3])*idetJ;
    }
-   const double idetJ = 1.0/detJ;
    const double R = inv_weight*rho0DetJ0w*idetJ;  // reference laghos_solver.cpp:1081 (inv_weight*rho0DetJ0w/detJ)
    const double E = fmax(0.0, e_q);
    const double P = (gamma - 1.0)*R*E;
-   const double S = sqrt(gamma*(gamma - 1.0)*E);
+   const double S = qm::fsqrt(gamma*(gamma - 1.0)*E);
 #pragma unroll
    for (int k = 0; k < DIM2; k++) { stress[k] = 0.0; }
 #pragma unroll
@@ -126,15 +126,16 @@ __device__ __forceinline__ double qpoint(const double *J, const double *dV, cons
          if (max_norm != 0.0)
          {
             double fnorm2 = 0.0;
+            const double imax_norm = qm::frcp(max_norm);
 #pragma unroll
-            for (int i = 0; i < DIM2; i++) { const double en = sg[i]/max_norm; fnorm2 += en*en; }
-            grad_norm = max_norm*sqrt(fnorm2);
+            for (int i = 0; i < DIM2; i++) { const double en = sg[i]*imax_norm; fnorm2 += en*en; }
+            grad_norm = max_norm*qm::fsqrt(fnorm2);
          }
          double tr = 0.0;
 #pragma unroll
          for (int i = 0; i < DIM; i++) { tr += sg[i + i*DIM]; }
          const double div_v = fabs(tr);
-         vorticity_coeff = (grad_norm > 0.0) ? div_v/grad_norm : 1.0;
+         vorticity_coeff = (grad_norm > 0.0) ? qm::fdiv(div_v, grad_norm) : 1.0;
       }
       // Symmetrize
 #pragma unroll
@@ -148,33 +149,31 @@ __device__ __forceinline__ double qpoint(const double *J, const double *dV, cons
       double mu, c0, c1, c2 = 0.0;
       if (DIM == 2) { qm::min_eig2(sg[0], sg[2], sg[3], mu, c0, c1); }
       else { qm::min_eig3(sg[0], sg[3], sg[6], sg[4], sg[7], sg[8], mu, c0, c1, c2); }
-      // Jpi = J * J0inv ; ph_dir = Jpi * compr_dir
+      // ph_dir = (J * J0inv) * compr_dir, evaluated as J * (J0inv * compr_dir)
       double ph[DIM];
       {
-         double Jpi[DIM2];
-#pragma unroll
-         for (int j = 0; j < DIM; j++)
-#pragma unroll
-            for (int i = 0; i < DIM; i++)
-            {
-               double a = 0.0;
-#pragma unroll
-               for (int k = 0; k < DIM; k++) { a += J[i + k*DIM]*J0inv[k + j*DIM]; }
-               Jpi[i + j*DIM] = a;
-            }
          const double cd[3] = {c0, c1, c2};
+         double t[DIM];
 #pragma unroll
          for (int i = 0; i < DIM; i++)
          {
             double a = 0.0;
 #pragma unroll
-            for (int j = 0; j < DIM; j++) { a += Jpi[i + j*DIM]*cd[j]; }
+            for (int j = 0; j < DIM; j++) { a += J0inv[i + j*DIM]*cd[j]; }
+            t[i] = a;
+         }
+#pragma unroll
+         for (int i = 0; i < DIM; i++)
+         {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < DIM; j++) { a += J[i + j*DIM]*t[j]; }
             ph[i] = a;
          }
       }
       const double ph_dir_nl2 = (DIM == 2) ? qm::norml2_2(ph[0], ph[1]) : qm::norml2_3(ph[0], ph[1], ph[DIM-1]);
       const double compr_dir_nl2 = (DIM == 2) ? qm::norml2_2(c0, c1) : qm::norml2_3(c0, c1, c2);
-      const double H = p.h0*ph_dir_nl2/compr_dir_nl2;
+      const double H = p.h0*qm::fdiv(ph_dir_nl2, compr_dir_nl2);
       visc_coeff = 2.0*R*H*H*fabs(mu);
       const double eps = 1e-12;
       visc_coeff += 0.5*R*H*S*vorticity_coeff*(1.0 - qm::smooth_step_01(mu - 2.0*eps, eps));
@@ -185,12 +184,12 @@ __device__ __forceinline__ double qpoint(const double *J, const double *dV, cons
                      : qm::min_sv3(J[0], J[1], J[2], J[3], J[DIM2 > 4 ? 4 : 0], J[DIM2 > 5 ? 5 : 0],
                                    J[DIM2 > 6 ? 6 : 0], J[DIM2 > 7 ? 7 : 0], J[DIM2 > 8 ? 8 : 0]);
    const double h_min = sv*p.inv_h1order;
-   const double ih_min = 1./h_min;
-   const double irho_ih_min_sq = ih_min*ih_min/R;
+   const double ih_min = qm::frcp(h_min);
+   const double irho_ih_min_sq = qm::fdiv(ih_min*ih_min, R);
    const double idt = S*ih_min + 2.5*visc_coeff*irho_ih_min_sq;
    double dt_q = p.dt_in;
    if (detJ < 0.0) { dt_q = 0.0; }
-   else if (idt > 0.0) { dt_q = fmin(dt_q, p.cfl/idt); }
+   else if (idt > 0.0) { dt_q = fmin(dt_q, qm::fdiv(p.cfl, idt)); }
    // stressJiT = stress * Jinv^T, scaled
    const double wd = weight*detJ;
 #pragma unroll

@@ -64,6 +64,34 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// Bulk asynchronous copy (TMA, 1D): one thread hands a contiguous, 16-byte aligned slab to the copy engine,
+// completion is counted in bytes on a shared-memory mbarrier (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+   const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned int bytes)
+{
+   const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned int bytes, uint64_t *bar)
+{
+   const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+   const unsigned int b = (unsigned int)__cvta_generic_to_shared(bar);
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned int parity)
+{
+   const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+   asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@!p bra WAIT_%=;\n\t}" :: "r"(a), "r"(parity) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // L2 (Bernstein) dofs -> values at quadrature points for NB elements.
 // Es[e][NL] -> Eq[e][NQ]; scratch t1[e][L*L*Q], t2[e][L*Q*Q].  Ends with a barrier.
@@ -201,7 +229,11 @@ struct QUpd3DCfg
    // dofs alias the stage-2 arrays (dead after the x pencils)
    static constexpr int S_A = (3*S_ST2 > S_DOF) ? 3*S_ST2 : S_DOF;
    static constexpr int S_TAB = 2*Q1D*D1D + Q1D*L1D;       // B, G, BL for the per-point z pass (runtime qz)
-   static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + 32 + S_TAB;
+   // the element's Jac0inv (9 NQ) and rho0DetJ0w (NQ) slabs, brought in by bulk asynchronous copies under
+   // the gather and the pencil stages; both are 16-byte multiples when NQ is even
+   static constexpr bool BULK = (NQ % 2 == 0);
+   static constexpr int S_SLAB = BULK ? 10*NQ : 0;
+   static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + 32 + S_TAB + S_SLAB + 2;
    static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES;
 };
 
@@ -215,14 +247,29 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
           const QPointParams prm, double *__restrict__ sJit, double *__restrict__ dt_block_min)
 {
    using C = QUpd3DCfg<D1D,Q1D>;
-   extern __shared__ double smem[];
+   extern __shared__ __align__(16) double smem[];
    double *A = smem;                            // dofs, later BB | GB | BG
    double *Bx = A + C::S_A, *Gx = Bx + C::S_ST1;
    double *E1 = Gx + C::S_ST1, *E2 = E1 + C::S_E1, *red = E2 + C::S_E2;
    double *TB = red + 32, *TG = TB + Q1D*D1D, *TBL = TG + Q1D*D1D;
+   // slabs at an even double offset from the (16-byte aligned) dynamic shared memory base
+   constexpr int SLAB_OFF = ((C::S_A + 2*C::S_ST1 + C::S_E1 + C::S_E2 + 32 + C::S_TAB + 1)/2)*2;
+   double *J0s = smem + SLAB_OFF, *Rs = J0s + 9*C::NQ;
+   __shared__ uint64_t mbar;
    const int tid = threadIdx.x;
    const int e = blockIdx.x;
    const size_t NEQ = (size_t)NE*C::NQ;
+   if (C::BULK)
+   {
+      if (tid == 0) { mbar_init(&mbar, 1); }
+      __syncthreads();
+      if (tid == 0)
+      {
+         mbar_expect_tx(&mbar, 10*C::NQ*(unsigned int)sizeof(double));
+         bulk_g2s(J0s, Jac0inv + (size_t)e*C::NQ*9, 9*C::NQ*(unsigned int)sizeof(double), &mbar);
+         bulk_g2s(Rs, rho0DetJ0w + (size_t)e*C::NQ, C::NQ*(unsigned int)sizeof(double), &mbar);
+      }
+   }
    for (int i = tid; i < Q1D*D1D; i += NT) { TB[i] = tab.B[i]; TG[i] = tab.G[i]; }
    for (int i = tid; i < Q1D*C::L1D; i += NT) { TBL[i] = tab.BL[i]; }
    // gather x, v (6 scalar fields: S = (x | v | e), field f at offset f*ndofs) and e
@@ -310,6 +357,7 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
    // z pass + point physics
    const double gam = gamma[e];
    double dt_min = prm.dt_in;
+   if (C::BULK) { mbar_wait(&mbar, 0); }
    for (int q = tid; q < C::NQ; q += NT)
    {
       const int col = q % C::QQ, qz = q / C::QQ;
@@ -331,20 +379,20 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
          else { dV[f - 3] = g0; dV[f] = g1; dV[f + 3] = g2; }
       }
       const size_t eq = (size_t)e*C::NQ + q;
-      double J0[9], sJ[9];
-      const double *j0 = Jac0inv + eq*9;
-#pragma unroll
-      for (int k = 0; k < 9; k++) { J0[k] = __ldg(j0 + k); }
+      double sJ[9];
+      const double *j0 = C::BULK ? J0s + 9*q : Jac0inv + eq*9;
       double e_q = 0.0;
 #pragma unroll
       for (int lz = 0; lz < C::L1D; lz++) { e_q += TBL[qz + Q1D*lz]*E2[col + C::QQ*lz]; }
-      const double dtq = qpoint<3>(J, dV, e_q, __ldg(rho0DetJ0w + eq), J0, gam, __ldg(qweights + q),
+      const double dtq = qpoint<3>(J, dV, e_q, C::BULK ? Rs[q] : __ldg(rho0DetJ0w + eq), j0, gam, __ldg(qweights + q),
                                    __ldg(inv_qweights + q), prm, sJ);
       dt_min = fmin(dt_min, dtq);
+      // one 64-bit address, advanced by the plane stride (the indexed form costs ~8 integer instructions per store)
+      double *sp = sJit + eq;
 #pragma unroll
       for (int vd = 0; vd < 3; vd++)
 #pragma unroll
-         for (int gd = 0; gd < 3; gd++) { sJit[eq + NEQ*(gd + vd*3)] = sJ[vd + gd*3]; }
+         for (int gd = 0; gd < 3; gd++) { *sp = sJ[vd + gd*3]; sp += NEQ; }
    }
    // block minimum (exact, order independent); NT is a whole number of warps
    for (int o = 16; o > 0; o >>= 1) { dt_min = fmin(dt_min, __shfl_xor_sync(0xffffffffu, dt_min, o)); }

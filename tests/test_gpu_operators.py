@@ -159,9 +159,19 @@ def test_cg_emass(pair):
     b = np.random.default_rng(13).uniform(-1, 1, P.ndofs_l2)
     xr, itr = O.cg_emass(b)
     for c in ctxs:
+        # the reference's solver: global unpreconditioned CG (lagb_tune_set key 10 = 1)
+        c.tune(10, 1)
         x, it = c.cg_emass(c.dev(b))
         assert abs(it - itr) <= 1
         assert relerr(x.cpu().numpy(), xr) < 1e-6
+        # default: element inverses built once: exact to round-off, so M x = b holds far
+        # below the CG tolerance and x agrees with the CG iterate to that tolerance
+        c.tune(10, 0)
+        xd, itd = c.cg_emass(c.dev(b))
+        assert itd == 0
+        # residual ~ cond(M_e) eps: the order-4 Bernstein mass matrix (Q5Q4) has cond ~ 1e5
+        assert relerr(c.emass_mult(xd).cpu().numpy(), b) < (1e-11 if P.L1D <= 4 else 1e-9)
+        assert relerr(xd.cpu().numpy(), xr) < 1e-6
 
 
 def test_taylor_source_2d(pair):

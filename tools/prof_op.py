@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--ok", type=int, default=3)
     ap.add_argument("--mesh", default="cube01_hex")
     ap.add_argument("--problem", type=int, default=1)
+    ap.add_argument("--sedov-steps", type=int, default=0,
+                    help="take the state after this many RK4 steps of the real run instead of the perturbed IC")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -37,6 +39,10 @@ def main():
     S = P.S0.copy()
     S[nv:2 * nv] = 0.01 * rng.uniform(-1, 1, nv)
     S[2 * nv:] = rng.uniform(0.5, 1.5, nl)
+    if args.sedov_steps > 0:
+        from laghos_b200.api import run
+        S = run(mesh=args.mesh, rs=args.rs, problem=args.problem, ok=args.ok, ot=args.ok - 1,
+                max_tsteps=args.sedov_steps, t_final=1e9, want_state=True)["S"]
     dS = c.dev(S)
     v = c.dev(rng.uniform(-1, 1, nv))
     e = c.dev(rng.uniform(0.5, 1.5, nl))
