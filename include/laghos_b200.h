@@ -192,6 +192,12 @@ int lagb_cg_emass(lagb_ctx *ctx, const double *d_b, double *d_x,
 int lagb_internal_energy(lagb_ctx *ctx, const double *d_e, double *h_out);
 int lagb_kinetic_energy(lagb_ctx *ctx, const double *d_v, double *h_out);
 
+/* LagrangianHydroOperator::ComputeDensity (laghos_solver.cpp:542-563): the L2 density field on the current
+ * mesh, per element rho_z = Mrho(x)^-1 rhs with the DensityIntegrator right-hand side
+ * (laghos_assembly.cpp:26-41).  Diagnostics path (visualisation / -err), synchronous.
+ * d_x: current mesh nodes (H1 vector); d_rho: [ndofs_l2]. */
+int lagb_compute_density(lagb_ctx *ctx, const double *d_x, double *d_rho);
+
 /* 2D Taylor-Green energy source (laghos_solver.cpp:455-465): d_esrc[ndofs_l2] */
 int lagb_taylor_source(lagb_ctx *ctx, const double *d_x, double *d_esrc);
 

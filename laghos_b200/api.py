@@ -253,6 +253,12 @@ class Context:
         _check(self.lib, self.lib.lagb_kinetic_energy(self.h, self._p(v), C.byref(out)))
         return out.value
 
+    def compute_density(self, x):
+        """LagrangianHydroOperator::ComputeDensity (laghos_solver.cpp:542-563): L2 density on the mesh x."""
+        rho = self.empty(self.P.ndofs_l2)
+        _check(self.lib, self.lib.lagb_compute_density(self.h, self._p(x), self._p(rho)))
+        return rho
+
     def taylor_source(self, x):
         e = self.empty(self.P.ndofs_l2)
         _check(self.lib, self.lib.lagb_taylor_source(self.h, self._p(x), self._p(e)))

@@ -48,6 +48,13 @@ static int timer_resolve(Ctx &c)
 }
 int timer_begin(Ctx &c, int w)
 {
+   if (c.timer.open[w] && !c.timer.pending[w].empty())
+   {
+      // an error return left this interval without its end event: drop it
+      auto p = c.timer.pending[w].back(); c.timer.pending[w].pop_back();
+      c.timer.pool.push_back(p.first); c.timer.pool.push_back(p.second);
+      c.timer.open[w] = false;
+   }
    cudaEvent_t a = timer_event(c), b = timer_event(c);
    LAGB_CUDA(cudaEventRecord(a, c.stream));
    c.timer.pending[w].push_back({a, b});
@@ -556,6 +563,16 @@ static int pcg_run(Ctx &c, bool l2, int nc, int comp0, const double *b, double *
 
 using namespace lagb;
 
+// every entry point that takes a context runs on the context's device (the caller may have changed
+// the current device between calls; one process can drive several contexts)
+static inline int enter(Ctx &c)
+{
+   int cur = -1;
+   if (cudaGetDevice(&cur) != cudaSuccess || cur != c.device) { LAGB_CUDA(cudaSetDevice(c.device)); }
+   return LAGB_OK;
+}
+#define LAGB_ENTER(h) do { if (!(h)) { set_error("null context"); return LAGB_ERR_INVALID; } int e__ = enter((h)->c); if (e__) { return e__; } } while (0)
+
 extern "C" {
 
 const char *lagb_last_error(void) { return g_err.c_str(); }
@@ -578,7 +595,12 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    c.ndofs = d->ndofs_h1; c.ndofs_l2 = (int64_t)c.NE*c.NL;
    c.use_visc = d->use_visc; c.use_vort = d->use_vort; c.variant = d->kernel_variant; c.device = d->device;
    c.stream = (cudaStream_t)stream;
-   { cudaDeviceProp prop; LAGB_CUDA(cudaGetDeviceProperties(&prop, d->device)); c.num_sms = prop.multiProcessorCount; }
+   {
+      int sms = 0;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device) != cudaSuccess)
+      { set_error("cudaDeviceGetAttribute(multiProcessorCount) failed"); delete h; return LAGB_ERR_CUDA; }
+      c.num_sms = sms;
+   }
    c.ks_generic = make_generic_kernels(c.dim, c.D1D, c.Q1D);
    if (!c.ks_generic.mass_h1)
    {
@@ -624,12 +646,19 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    rc |= dev_alloc(&c.d_tmp, 16); rc |= dev_alloc(&c.d_dt, 1); rc |= dev_alloc(&c.d_elem_vol, (size_t)c.NE);
    rc |= dev_alloc(&c.d_state, 1);
    if (rc) { lagb_ctx_destroy(h); return LAGB_ERR_CUDA; }
-   LAGB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-   LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
-   LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
-   LAGB_CUDA(cudaMallocHost((void**)&c.h_state, sizeof(pcg::State)));
-   LAGB_CUDA(cudaMallocHost((void**)&c.h_scal, 16*sizeof(double)));
-   LAGB_CUDA(cudaMemset(c.d_sJit, 0, NEQ*D2*sizeof(double)));
+   // late failures release what was allocated so far (lagb_ctx_destroy accepts a partly built context)
+   auto finish = [&]() -> int
+   {
+      LAGB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+      LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
+      LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+      LAGB_CUDA(cudaMallocHost((void**)&c.h_state, sizeof(pcg::State)));
+      LAGB_CUDA(cudaMallocHost((void**)&c.h_scal, 16*sizeof(double)));
+      LAGB_CUDA(cudaMemset(c.d_sJit, 0, NEQ*D2*sizeof(double)));
+      return LAGB_OK;
+   };
+   rc = finish();
+   if (rc) { lagb_ctx_destroy(h); return rc; }
    *out = h;
    return LAGB_OK;
 }
@@ -665,6 +694,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
 
 int lagb_ctx_sync(lagb_ctx *h)
 {
+   LAGB_ENTER(h);
    LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
    if (h->c.copy_stream) { LAGB_CUDA(cudaStreamSynchronize(h->c.copy_stream)); }
    return LAGB_OK;
@@ -673,6 +703,7 @@ int lagb_ctx_sync(lagb_ctx *h)
 int lagb_setup_qdata0(lagb_ctx *h, const double *d_x0, const double *d_rho0_gf, const double *d_rho0_q,
                       int64_t ne_global, double *h0_out)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    int rc = ks.rho0detj0(c, d_x0, d_rho0_gf, d_rho0_q, c.d_elem_vol); if (rc) { return rc; }
@@ -710,6 +741,7 @@ int lagb_setup_qdata0(lagb_ctx *h, const double *d_x0, const double *d_rho0_gf, 
 
 int lagb_vmass_mult(lagb_ctx *h, int comp, const double *d_x, double *d_y)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (comp >= c.dim) { set_error("vmass_mult: bad component"); return LAGB_ERR_INVALID; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
@@ -731,6 +763,7 @@ int lagb_vmass_mult(lagb_ctx *h, int comp, const double *d_x, double *d_y)
 
 int lagb_vmass_mult_all(lagb_ctx *h, const double *d_x, double *d_y)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    int rc;
@@ -768,6 +801,7 @@ int lagb_tune_set(lagb_ctx *h, int key, int value)
 
 int lagb_vmass_diag(lagb_ctx *h, double *d_diag)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("vmass_diag: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    LAGB_CUDA(cudaMemcpyAsync(d_diag, c.d_diag, sizeof(double)*c.ndofs, cudaMemcpyDeviceToDevice, c.stream));
@@ -776,6 +810,7 @@ int lagb_vmass_diag(lagb_ctx *h, double *d_diag)
 
 int lagb_emass_mult(lagb_ctx *h, const double *d_x, double *d_y)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    return ks.mass_l2(c, d_x, d_y);
@@ -783,6 +818,7 @@ int lagb_emass_mult(lagb_ctx *h, const double *d_x, double *d_y)
 
 int lagb_force_mult(lagb_ctx *h, const double *d_e, double *d_v)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    int rc = timer_begin(c, 2); if (rc) { return rc; }
@@ -794,6 +830,7 @@ int lagb_force_mult(lagb_ctx *h, const double *d_e, double *d_v)
 
 int lagb_force_mult_transpose(lagb_ctx *h, const double *d_v, double *d_e)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    int rc = timer_begin(c, 2); if (rc) { return rc; }
@@ -803,6 +840,7 @@ int lagb_force_mult_transpose(lagb_ctx *h, const double *d_v, double *d_e)
 
 int lagb_dt_est_set(lagb_ctx *h, double v)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    pcg::vec_fill<<<1, 32, 0, c.stream>>>(c.d_dt, v, 1);
    LAGB_LAUNCH_CHECK();
@@ -811,6 +849,7 @@ int lagb_dt_est_set(lagb_ctx *h, double v)
 
 int lagb_qupdate_async(lagb_ctx *h, const double *d_S, double cfl)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("qupdate: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
@@ -826,6 +865,7 @@ int lagb_qupdate_async(lagb_ctx *h, const double *d_S, double cfl)
 
 int lagb_dt_est_read(lagb_ctx *h, double *out)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    int rc = allreduce_min(c, c.d_dt, 1); if (rc) { return rc; }
    LAGB_CUDA(cudaMemcpyAsync(c.h_scal, c.d_dt, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -836,6 +876,7 @@ int lagb_dt_est_read(lagb_ctx *h, double *out)
 
 int lagb_qupdate(lagb_ctx *h, const double *d_S, double cfl, double dt_est_in, double *out)
 {
+   LAGB_ENTER(h);
    int rc = lagb_dt_est_set(h, dt_est_in); if (rc) { return rc; }
    rc = lagb_qupdate_async(h, d_S, cfl); if (rc) { return rc; }
    return lagb_dt_est_read(h, out);
@@ -843,6 +884,7 @@ int lagb_qupdate(lagb_ctx *h, const double *d_S, double cfl, double dt_est_in, d
 
 int lagb_pcg_vmass(lagb_ctx *h, int comp, const double *d_b, double *d_x, double rel_tol, int max_iter, int *iters)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("pcg_vmass: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    if (comp < 0 || comp >= c.dim) { set_error("pcg_vmass: bad component"); return LAGB_ERR_INVALID; }
@@ -857,6 +899,7 @@ int lagb_pcg_vmass(lagb_ctx *h, int comp, const double *d_b, double *d_x, double
 
 int lagb_pcg_vmass_all(lagb_ctx *h, const double *d_rhs, double *d_dv, double rel_tol, int max_iter, int *iters)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("pcg_vmass_all: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    int rc = timer_begin(c, 0); if (rc) { return rc; }
@@ -869,6 +912,7 @@ int lagb_pcg_vmass_all(lagb_ctx *h, const double *d_rhs, double *d_dv, double re
 
 int lagb_cg_emass(lagb_ctx *h, const double *d_b, double *d_x, double rel_tol, int max_iter, int *iters)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("cg_emass: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    int rc = timer_begin(c, 1); if (rc) { return rc; }
@@ -908,6 +952,7 @@ static int global_dot(Ctx &c, const double *a, const double *b, int64_t n, doubl
 
 int lagb_internal_energy(lagb_ctx *h, const double *d_e, double *h_out)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("internal_energy: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
@@ -919,6 +964,7 @@ int lagb_internal_energy(lagb_ctx *h, const double *d_e, double *h_out)
 
 int lagb_kinetic_energy(lagb_ctx *h, const double *d_v, double *h_out)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (!c.setup_done) { set_error("kinetic_energy: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
@@ -933,8 +979,24 @@ int lagb_kinetic_energy(lagb_ctx *h, const double *d_v, double *h_out)
    return LAGB_OK;
 }
 
+int lagb_compute_density(lagb_ctx *h, const double *d_x, double *d_rho)
+{
+   LAGB_ENTER(h);
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("compute_density: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   if (c.L1D < 1) { set_error("compute_density: needs a thermodynamic space"); return LAGB_ERR_INVALID; }
+   double *wdet = nullptr;
+   LAGB_CUDA(cudaMalloc((void**)&wdet, sizeof(double)*(size_t)c.NE*c.NQ));
+   int rc = c.ks_generic.detj_w(c, d_x, wdet);
+   if (!rc) { rc = density_project(c, wdet, d_rho); }
+   cudaStreamSynchronize(c.stream);
+   cudaFree(wdet);
+   return rc;
+}
+
 int lagb_taylor_source(lagb_ctx *h, const double *d_x, double *d_esrc)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (c.dim != 2) { set_error("taylor_source: 2D only (reference laghos.cpp:638)"); return LAGB_ERR_INVALID; }
    return c.ks_generic.taylor(c, d_x, d_esrc);
@@ -955,6 +1017,7 @@ int lagb_qdata_set_h0(lagb_ctx *h, double h0) { h->c.h0 = h0; return LAGB_OK; }
 
 int lagb_dev_malloc(lagb_ctx *h, double **d_out, int64_t n)
 {
+   LAGB_ENTER(h);
    (void)h;
    LAGB_CUDA(cudaMalloc((void**)d_out, std::max<int64_t>(n, 1)*sizeof(double)));
    return LAGB_OK;
@@ -962,23 +1025,27 @@ int lagb_dev_malloc(lagb_ctx *h, double **d_out, int64_t n)
 int lagb_dev_free(lagb_ctx *h, double *p) { (void)h; LAGB_CUDA(cudaFree(p)); return LAGB_OK; }
 int lagb_memcpy_h2d(lagb_ctx *h, double *d_dst, const double *h_src, int64_t n)
 {
+   LAGB_ENTER(h);
    LAGB_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double)*n, cudaMemcpyHostToDevice, h->c.stream));
    LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
    return LAGB_OK;
 }
 int lagb_memcpy_h2d_async(lagb_ctx *h, double *d_dst, const double *h_src, int64_t n)
 {
+   LAGB_ENTER(h);
    LAGB_CUDA(cudaMemcpyAsync(d_dst, h_src, sizeof(double)*n, cudaMemcpyHostToDevice, h->c.stream));
    return LAGB_OK;
 }
 int lagb_memcpy_d2h(lagb_ctx *h, double *h_dst, const double *d_src, int64_t n)
 {
+   LAGB_ENTER(h);
    LAGB_CUDA(cudaMemcpyAsync(h_dst, d_src, sizeof(double)*n, cudaMemcpyDeviceToHost, h->c.stream));
    LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
    return LAGB_OK;
 }
 int lagb_memcpy_h2d_bg(lagb_ctx *h, double *d_dst, const double *h_src, int64_t n)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    LAGB_CUDA(cudaEventRecord(c.ev_compute, c.stream));
    LAGB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_compute, 0));
@@ -988,6 +1055,7 @@ int lagb_memcpy_h2d_bg(lagb_ctx *h, double *d_dst, const double *h_src, int64_t 
 }
 int lagb_memcpy_d2h_bg(lagb_ctx *h, double *h_dst, const double *d_src, int64_t n)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    LAGB_CUDA(cudaEventRecord(c.ev_compute, c.stream));
    LAGB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.ev_compute, 0));
@@ -997,6 +1065,7 @@ int lagb_memcpy_d2h_bg(lagb_ctx *h, double *h_dst, const double *d_src, int64_t 
 }
 int lagb_wait_copies(lagb_ctx *h)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    LAGB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_copy, 0));
    return LAGB_OK;
@@ -1010,6 +1079,7 @@ int lagb_host_free_pinned(double *p) { LAGB_CUDA(cudaFreeHost(p)); return LAGB_O
 
 int lagb_vec_fill(lagb_ctx *h, double *y, double a, int64_t n)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    pcg::vec_fill<<<vec_grid(n), pcg::RB, 0, c.stream>>>(y, a, n);
    LAGB_LAUNCH_CHECK();
@@ -1017,11 +1087,13 @@ int lagb_vec_fill(lagb_ctx *h, double *y, double a, int64_t n)
 }
 int lagb_vec_copy(lagb_ctx *h, double *y, const double *x, int64_t n)
 {
+   LAGB_ENTER(h);
    LAGB_CUDA(cudaMemcpyAsync(y, x, sizeof(double)*n, cudaMemcpyDeviceToDevice, h->c.stream));
    return LAGB_OK;
 }
 int lagb_vec_axpby(lagb_ctx *h, double *z, double a, const double *x, double b, const double *y, int64_t n)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    pcg::vec_axpby<<<vec_grid(n), pcg::RB, 0, c.stream>>>(z, a, x, b, y ? y : x, n);
    LAGB_LAUNCH_CHECK();
@@ -1029,6 +1101,7 @@ int lagb_vec_axpby(lagb_ctx *h, double *z, double a, const double *x, double b, 
 }
 int lagb_vec_dot(lagb_ctx *h, const double *x, const double *y, int64_t n, double *out)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    const int g = vec_grid(n);
    pcg::dot_partial<1><<<g, pcg::RB, 0, c.stream>>>(n, 0, x, y, nullptr, c.d_part);
@@ -1053,6 +1126,7 @@ int lagb_ctx_comm_init(lagb_ctx *h, const uint8_t id[128], int rank, int nranks,
                        const int32_t *nshared, const int32_t *const *h_shared_dofs,
                        const uint8_t *h_owner_mask)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    int rc = nccl_load(); if (rc) { return rc; }
    Uid128 uid; memcpy(uid.internal, id, 128);
@@ -1113,6 +1187,7 @@ int lagb_ctx_comm_init(lagb_ctx *h, const uint8_t id[128], int rank, int nranks,
 
 int lagb_allreduce_host(lagb_ctx *h, double *vals, int n, int op)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (c.nranks <= 1) { return LAGB_OK; }
    if (n > 8) { set_error("allreduce_host: n > 8"); return LAGB_ERR_INVALID; }
@@ -1128,6 +1203,7 @@ int lagb_allreduce_host(lagb_ctx *h, double *vals, int n, int op)
 
 int lagb_timing_get(lagb_ctx *h, lagb_timing *out)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    int rc = timer_resolve(c); if (rc) { return rc; }
    out->t_cgH1 = c.timer.acc[0]; out->t_cgL2 = c.timer.acc[1]; out->t_force = c.timer.acc[2]; out->t_qdata = c.timer.acc[3];
@@ -1136,6 +1212,7 @@ int lagb_timing_get(lagb_ctx *h, lagb_timing *out)
 }
 int lagb_timing_reset(lagb_ctx *h)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    int rc = timer_resolve(c); if (rc) { return rc; }
    for (int w = 0; w < Timer::NT; w++) { c.timer.acc[w] = 0.0; }
@@ -1146,6 +1223,7 @@ int lagb_timing_reset(lagb_ctx *h)
 int lagb_profile_mass(lagb_ctx *h, int enable) { h->c.profile_mass = enable != 0; return LAGB_OK; }
 int lagb_profile_mass_get(lagb_ctx *h, double *seconds, int64_t *launches)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    int rc = timer_resolve(c); if (rc) { return rc; }
    if (seconds) { *seconds = c.timer.acc[4]; }
@@ -1154,6 +1232,7 @@ int lagb_profile_mass_get(lagb_ctx *h, double *seconds, int64_t *launches)
 }
 int lagb_stopwatch_start(lagb_ctx *h)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    int rc = timer_resolve(c); if (rc) { return rc; }
    c.timer.acc[5] = 0.0;
@@ -1161,6 +1240,7 @@ int lagb_stopwatch_start(lagb_ctx *h)
 }
 int lagb_stopwatch_stop(lagb_ctx *h, double *seconds)
 {
+   LAGB_ENTER(h);
    Ctx &c = h->c;
    if (c.timer.pending[5].empty()) { set_error("stopwatch_stop without start"); return LAGB_ERR_STATE; }
    int rc = timer_end(c, 5); if (rc) { return rc; }

@@ -54,6 +54,7 @@ struct KernelSet
    int (*qupdate)(Ctx&, const double *S, const QPointParams &prm) = nullptr; // writes dt_part, sets dt_nblocks
    int (*rho0detj0)(Ctx&, const double *x0, const double *rho0_gf, const double *rho0_q, double *elem_vol) = nullptr;
    int (*taylor)(Ctx&, const double *x, double *esrc) = nullptr;
+   int (*detj_w)(Ctx&, const double *x, double *out) = nullptr;     // w detJ on the current mesh, [NE*NQ]
    bool tuned_mass = false;
 };
 
@@ -139,7 +140,8 @@ int halo_sum(Ctx &c, double *v, int nc);              // sum shared dofs across 
 int allreduce_sum(Ctx &c, double *d_vals, int n);     // in-stream
 int allreduce_min(Ctx &c, double *d_vals, int n);
 
-int l2_direct_solve(Ctx &c, const double *b, double *x, bool *done);   // kernels_l2.cu; *done = false: not available
+int l2_direct_solve(Ctx &c, const double *b, double *x, bool *done);
+int density_project(Ctx &c, const double *wdet, double *rho);        // kernels_l2.cu: ComputeDensity's element solves   // kernels_l2.cu; *done = false: not available
 int get_plan(Ctx &c, int NB, DevPlan **out);    // brick schedule for NB elements per batch and the shape c.tune[7] (built on first use)
 
 KernelSet make_generic_kernels(int dim, int D1D, int Q1D);

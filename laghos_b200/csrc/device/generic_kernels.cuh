@@ -409,6 +409,43 @@ __global__ void rho0detj0(const __grid_constant__ DevTables<D1D,Q1D> tab, int NE
    }
 }
 
+// w(q) detJ(q) on the CURRENT mesh: the coefficient of MassIntegrator in ComputeDensity
+// (reference laghos_solver.cpp:542-563); a diagnostics path (visualisation, -err), not timed.
+template<int DIM, int D1D, int Q1D>
+__global__ void detj_w(const __grid_constant__ DevTables<D1D,Q1D> tab, int NE, int64_t ndofs,
+                       const int *__restrict__ map, const double *__restrict__ x,
+                       const double *__restrict__ qweights, double *__restrict__ out)
+{
+   using Dm = Dims<DIM,D1D,Q1D>;
+   using PE = PlaneEval<DIM,D1D,Q1D>;
+   for (int e = blockIdx.x*blockDim.x + threadIdx.x; e < NE; e += gridDim.x*blockDim.x)
+   {
+      double X[DIM][Dm::ND];
+      double WB[DIM][PE::DD], WG[DIM][PE::DD];
+      const int *m = map + (size_t)e*Dm::ND;
+      for (int c = 0; c < DIM; c++)
+         for (int i = 0; i < Dm::ND; i++) { X[c][i] = x[(size_t)c*ndofs + m[i]]; }
+      for (int qz = 0; qz < Dm::QZ; qz++)
+      {
+         for (int c = 0; c < DIM; c++) { PE::zplane(tab, qz, X[c], WB[c], WG[c]); }
+         for (int qy = 0; qy < Q1D; qy++)
+            for (int qx = 0; qx < Q1D; qx++)
+            {
+               const int q = qx + Q1D*(qy + Q1D*qz);
+               double J[DIM*DIM], g[3], val;
+               for (int c = 0; c < DIM; c++)
+               {
+                  PE::point(tab, qx, qy, WB[c], WG[c], g, val);
+                  for (int d = 0; d < DIM; d++) { J[c + DIM*d] = g[d]; }
+               }
+               const double det = (DIM == 2) ? J[0]*J[3] - J[1]*J[2]
+                                  : J[0]*(J[4]*J[DIM*DIM-1] - J[5]*J[7]) + J[3]*(J[2]*J[7] - J[1]*J[DIM*DIM-1]) + J[6]*(J[1]*J[5] - J[2]*J[4]);
+               out[(size_t)e*Dm::NQ + q] = qweights[q]*det;
+            }
+      }
+   }
+}
+
 // 2D Taylor-Green source (reference laghos_solver.cpp:455-465, laghos_solver.hpp:208-218)
 template<int DIM, int D1D, int Q1D>
 __global__ void taylor_source(const __grid_constant__ DevTables<D1D,Q1D> tab, int NE, int64_t ndofs,

@@ -84,6 +84,73 @@ l2inv_build(const int dim, const int L1D, const int Q1D, const double *__restric
    }
 }
 
+// Reference ComputeDensity (laghos_solver.cpp:542-563): per element rho_z = Mrho^-1 rhs with
+// Mrho = sum_q wdet(q) phi_i phi_j (mass matrix on the current mesh) and rhs_i = sum_q rho0DetJ0w(q) phi_i
+// (DensityIntegrator, laghos_assembly.cpp:26-41).  One CTA per element, same assembly and in-place
+// Gauss-Jordan as l2inv_build; a diagnostics path (visualisation, -err).
+__global__ void __launch_bounds__(256)
+density_project(const int dim, const int L1D, const int Q1D, const double *__restrict__ BL,
+                const double *__restrict__ wdet, const double *__restrict__ rho0DetJ0w, double *__restrict__ rho)
+{
+   extern __shared__ double sm[];
+   const int NL = (dim == 3) ? L1D*L1D*L1D : L1D*L1D;
+   const int NQ = (dim == 3) ? Q1D*Q1D*Q1D : Q1D*Q1D;
+   double *A = sm, *colk = A + NL*NL, *sBL = colk + NL, *sD = sBL + Q1D*L1D, *sR = sD + NQ, *rhs = sR + NQ;
+   const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+   const int QZ = (dim == 3) ? Q1D : 1;
+   for (int i = tid; i < Q1D*L1D; i += nt) { sBL[i] = BL[i]; }
+   for (int q = tid; q < NQ; q += nt) { sD[q] = wdet[(size_t)e*NQ + q]; sR[q] = rho0DetJ0w[(size_t)e*NQ + q]; }
+   __syncthreads();
+   for (int p = tid; p < NL*NL + NL; p += nt)
+   {
+      const bool is_rhs = p >= NL*NL;
+      const int i = is_rhs ? p - NL*NL : p / NL, j = is_rhs ? -1 : p - i*NL;
+      if (!is_rhs && j > i) { continue; }
+      const int ix = i % L1D, iy = (i / L1D) % L1D, iz = i / (L1D*L1D);
+      const int jx = is_rhs ? 0 : j % L1D, jy = is_rhs ? 0 : (j / L1D) % L1D, jz = is_rhs ? 0 : j / (L1D*L1D);
+      const double *coef = is_rhs ? sR : sD;
+      double acc = 0.0;
+      for (int qz = 0; qz < QZ; qz++)
+      {
+         const double bz = (dim == 3) ? sBL[qz + Q1D*iz]*(is_rhs ? 1.0 : sBL[qz + Q1D*jz]) : 1.0;
+         for (int qy = 0; qy < Q1D; qy++)
+         {
+            const double byz = bz*sBL[qy + Q1D*iy]*(is_rhs ? 1.0 : sBL[qy + Q1D*jy]);
+            const double *d = coef + Q1D*(qy + Q1D*qz);
+            double row = 0.0;
+            for (int qx = 0; qx < Q1D; qx++) { row += sBL[qx + Q1D*ix]*(is_rhs ? 1.0 : sBL[qx + Q1D*jx])*d[qx]; }
+            acc += byz*row;
+         }
+      }
+      if (is_rhs) { rhs[i] = acc; }
+      else { A[i*NL + j] = acc; A[j*NL + i] = acc; }
+   }
+   __syncthreads();
+   for (int k = 0; k < NL; k++)
+   {
+      const double piv = 1.0/A[k*NL + k];
+      __syncthreads();
+      for (int i = tid; i < NL; i += nt) { colk[i] = A[i*NL + k]; }
+      __syncthreads();
+      for (int j = tid; j < NL; j += nt) { A[k*NL + j] = (j == k) ? piv : A[k*NL + j]*piv; }
+      __syncthreads();
+      for (int p = tid; p < NL*NL; p += nt)
+      {
+         const int i = p / NL, j = p - i*NL;
+         if (i == k) { continue; }
+         const double base = (j == k) ? 0.0 : A[p];
+         A[p] = base - colk[i]*A[k*NL + j];
+      }
+      __syncthreads();
+   }
+   for (int i = tid; i < NL; i += nt)
+   {
+      double r = 0.0;
+      for (int j = 0; j < NL; j++) { r += A[i*NL + j]*rhs[j]; }
+      rho[(size_t)e*NL + i] = r;
+   }
+}
+
 // y[e][i] = sum_j Minv[e][j][i] x[e][j]; EPB elements per CTA, NLC = compile-time NL (0: runtime)
 template<int NLC, int EPB>
 __global__ void __launch_bounds__(NLC > 0 ? ((NLC*EPB + 31)/32)*32 : 256)

@@ -418,6 +418,7 @@ struct Problem
       // Sedov: vertex closest to the origin and the elements owning it
       // (MFEM GridFunction::ProjectDeltaCoefficient, not in tree)
       int vnear[3] = {0, 0, 0};
+      double dist2 = 0.0;
       for (int d = 0; d < dim; d++)
       {
          double best = 1e300;
@@ -425,7 +426,11 @@ struct Problem
          {
             if (fabs(mesh.brk[d][i]) < best) { best = fabs(mesh.brk[d][i]); vnear[d] = (int)i; }
          }
+         dist2 += best*best;
       }
+      // the reference only accepts a vertex within -dtol (default 1e-12, laghos.cpp:147, :605) of the blast position
+      if (sp.problem == 1 && !(sqrt(dist2) <= 1e-12))
+      { throw std::runtime_error("Delta function could not be initialized: no mesh vertex within delta_tol of the blast position"); }
       // unit-weight mass integral of the nodal interpolant over ALL (global) elements
       // that own the vertex: sum_q w detJ f(q); f is a tensor polynomial of degree ot,
       // so Gauss-Legendre(Q1D) is exact.

@@ -70,12 +70,18 @@ struct GenericLaunch
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
+   static int detj_w(Ctx &c, const double *x, double *out)
+   {
+      generic::detj_w<DIM,D1D,Q1D><<<grid(c), BS, 0, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, x, c.d_qweights, out);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
    static KernelSet make()
    {
       KernelSet k;
       k.mass_h1 = &mass_h1; k.mass_diag = &mass_diag; k.mass_l2 = &mass_l2;
       k.force_mult = &force_mult; k.force_mult_t = &force_mult_t; k.qupdate = &qupdate;
-      k.rho0detj0 = &rho0detj0; k.taylor = &taylor;
+      k.rho0detj0 = &rho0detj0; k.taylor = &taylor; k.detj_w = &detj_w;
       return k;
    }
 };

@@ -6,6 +6,8 @@
 
 namespace lagb {
 
+static int ensure_BL(Ctx &c);
+
 // Builds the element inverses on first use.  They cost NE*NL^2 doubles (Q3Q2 at 64^3 elements: 1.5 GB);
 // when that does not fit comfortably in free device memory the caller falls back to the CG.
 static int l2_build(Ctx &c)
@@ -20,13 +22,31 @@ static int l2_build(Ctx &c)
    const size_t smem = sizeof(double)*(NL2 + c.NL + (size_t)c.Q1D*c.L1D + c.NQ);
    if (smem > 200*1024) { return LAGB_OK; }
    LAGB_CUDA(cudaMalloc((void**)&c.d_l2inv, std::max<size_t>(need, 8)));
-   LAGB_CUDA(cudaMalloc((void**)&c.d_BL, sizeof(double)*c.Q1D*c.L1D));
-   const double *hBL = reinterpret_cast<const double*>(c.tab_blob.data()) + 2*c.Q1D*c.D1D;
-   LAGB_CUDA(cudaMemcpyAsync(c.d_BL, hBL, sizeof(double)*c.Q1D*c.L1D, cudaMemcpyHostToDevice, c.stream));
+   { int rc = ensure_BL(c); if (rc) { return rc; } }
    LAGB_CUDA(cudaFuncSetAttribute(l2::l2inv_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
    l2::l2inv_build<<<c.NE, 256, smem, c.stream>>>(c.dim, c.L1D, c.Q1D, c.d_BL, c.d_massD, c.d_l2inv);
    LAGB_LAUNCH_CHECK();
    c.l2inv_state = 1;
+   return LAGB_OK;
+}
+
+static int ensure_BL(Ctx &c)
+{
+   if (c.d_BL) { return LAGB_OK; }
+   LAGB_CUDA(cudaMalloc((void**)&c.d_BL, sizeof(double)*c.Q1D*std::max(1, c.L1D)));
+   const double *hBL = reinterpret_cast<const double*>(c.tab_blob.data()) + 2*c.Q1D*c.D1D;
+   LAGB_CUDA(cudaMemcpyAsync(c.d_BL, hBL, sizeof(double)*c.Q1D*c.L1D, cudaMemcpyHostToDevice, c.stream));
+   return LAGB_OK;
+}
+
+int density_project(Ctx &c, const double *wdet, double *rho)
+{
+   int rc = ensure_BL(c); if (rc) { return rc; }
+   const size_t smem = sizeof(double)*((size_t)c.NL*c.NL + 2*c.NL + (size_t)c.Q1D*c.L1D + 2*c.NQ);
+   if (smem > 200*1024) { set_error("compute_density: element matrix does not fit shared memory"); return LAGB_ERR_INVALID; }
+   LAGB_CUDA(cudaFuncSetAttribute(l2::density_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   l2::density_project<<<c.NE, 256, smem, c.stream>>>(c.dim, c.L1D, c.Q1D, c.d_BL, wdet, c.d_rho0DetJ0w, rho);
+   LAGB_LAUNCH_CHECK();
    return LAGB_OK;
 }
 

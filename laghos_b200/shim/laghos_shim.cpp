@@ -252,6 +252,30 @@ void RK4Solver::Step(Vector &x, double &t, double &dt)
    add(z, dt/6, k, x);
    t += dt;
 }
+void RK6Solver::Init(TimeDependentOperator &f_) { ODESolver::Init(f_); }
+void RK6Solver::Step(Vector &x, double &t, double &dt)
+{
+   static const double a[28] = {.6e-1,
+   .1923996296296296296296296296296296296296e-1, .7669337037037037037037037037037037037037e-1,
+   .35975e-1, 0., .107925,
+   1.318683415233148260919747276431735612861, 0., -5.042058063628562225427761634715637693344, 4.220674648395413964508014358283902080483,
+   -41.87259166432751461803757780644346812905, 0., 159.4325621631374917700365669070346830453, -122.1192135650100309202516203389242140663, 5.531743066200053768252631238332999150076,
+   -54.43015693531650433250642051294142461271, 0., 207.0672513650184644273657173866509835987, -158.6108137845899991828742424365058599469, 6.991816585950242321992597280791793907096, -.1859723106220323397765171799549294623692e-1,
+   -54.66374178728197680241215648050386959351, 0., 207.9528062553893734515824816699834244238, -159.2889574744995071508959805871426654216, 7.018743740796944434698170760964252490817, -.1833878590504572306472782005141738268361e-1, -.5119484997882099077875432497245168395840e-3};
+   static const double b[8] = {.3438957868357036009278820124728322386520e-1, 0., 0., .2582624555633503404659558098586120858767, .4209371189673537150642551514069801967032,
+   4.405396469669310170148836816197095664891, -176.4831190242986576151740942499002125029, 172.3641334014150730294022582711902413315};
+   static const double c[7] = {.6e-1, .9593333333333333333333333333333333333333e-1, .1439, .4973, .9725, .9995, 1.};
+   if (y.Size() != x.Size()) { y.SetSize(x.Ctx(), x.Size()); for (auto &ki : k) { ki.SetSize(x.Ctx(), x.Size()); } }
+   f->SetTime(t); f->Mult(x, k[0]);
+   for (int l = 0, i = 1; i < 8; i++)
+   {
+      add(x, a[l++]*dt, k[0], y);
+      for (int j = 1; j < i; j++) { y.Add(a[l++]*dt, k[j]); }
+      f->SetTime(t + c[i - 1]*dt); f->Mult(y, k[i]);
+   }
+   for (int i = 0; i < 8; i++) { x.Add(b[i]*dt, k[i]); }
+   t += dt;
+}
 void HydroODESolver::Init(TimeDependentOperator &f_)
 {
    ODESolver::Init(f_);
@@ -370,6 +394,7 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          case 2: ode_solver = new RK2Solver(0.5); stages = 2; break;
          case 3: ode_solver = new RK3SSPSolver; stages = 3; break;
          case 4: ode_solver = new RK4Solver; stages = 4; break;
+         case 6: ode_solver = new RK6Solver; stages = 8; break;
          case 7: ode_solver = new RK2AvgSolver; stages = 2; break;
          default: fprintf(stderr, "Unknown ODE solver type: %d\n", opt->ode_solver_type); lagb_ctx_destroy(ctx); return 3;
       }

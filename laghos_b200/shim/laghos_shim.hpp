@@ -196,6 +196,8 @@ public:
    // reference laghos_solver.cpp:639-697 (the MPI_Allreduce is inside the C-ABI call)
    double InternalEnergy(const Vector &e) const { double v; LAGHOS_CHECK(lagb_internal_energy(ctx, e.Read(), &v)); return v; }
    double KineticEnergy(const Vector &v_) const { double v; LAGHOS_CHECK(lagb_kinetic_energy(ctx, v_.Read(), &v)); return v; }
+   // reference laghos_solver.cpp:542-563 (x: the mesh nodes the density is evaluated on; rho: L2 vector)
+   void ComputeDensity(const Vector &x, Vector &rho) const { LAGHOS_CHECK(lagb_compute_density(ctx, x.Read(), rho.Write())); }
    void StatePending() const { state_pending = true; }
    void WaitState() const { if (state_pending) { LAGHOS_CHECK(lagb_wait_copies(ctx)); state_pending = false; } }
    void UpdateQuadratureData(const Vector &S) const;
@@ -220,6 +222,8 @@ class ForwardEulerSolver : public ODESolver { Vector dxdt; public: void Init(Tim
 class RK2Solver : public ODESolver { double a; Vector dxdt, x1; public: RK2Solver(double a_ = 2./3.) : a(a_) { } void Init(TimeDependentOperator &f_) override; void Step(Vector &x, double &t, double &dt) override; };
 class RK3SSPSolver : public ODESolver { Vector y, k; public: void Init(TimeDependentOperator &f_) override; void Step(Vector &x, double &t, double &dt) override; };
 class RK4Solver : public ODESolver { Vector y, k, z; public: void Init(TimeDependentOperator &f_) override; void Step(Vector &x, double &t, double &dt) override; };
+// MFEM ExplicitRKSolver with the RK6Solver tables (8 stages, 6th order; reference laghos.cpp:529, -s 6)
+class RK6Solver : public ODESolver { Vector y, k[8]; public: void Init(TimeDependentOperator &f_) override; void Step(Vector &x, double &t, double &dt) override; };
 // reference laghos_solver.hpp:232-255, laghos_solver.cpp:1429-1487
 class HydroODESolver : public ODESolver
 {

@@ -177,6 +177,63 @@ struct Kernels
       }
       return sum;
    }
+   // reference LagrangianHydroOperator::ComputeDensity (laghos_solver.cpp:542-563): per element
+   // rho_z = Mrho^-1 rhs with Mrho = MassIntegrator on the CURRENT mesh (sum_q w detJ phi_i phi_j) and
+   // rhs_i = sum_q rho0DetJ0w phi_i (DensityIntegrator, laghos_assembly.cpp:26-41); dense LU with partial
+   // pivoting like MFEM's DenseMatrixInverse.
+   static void ComputeDensity(const Problem &P, const double *x, const double *rho0DetJ0w, double *rho)
+   {
+      const double *BL = P.tab.BL.data();
+      std::vector<double> phi((size_t)NL*NQ);
+      for (int i = 0; i < NL; i++)
+      {
+         double unit[NL];
+         for (int k = 0; k < NL; k++) { unit[k] = (k == i) ? 1.0 : 0.0; }
+         interp<L1D>(BL, unit, phi.data() + (size_t)i*NQ);
+      }
+      for (int e = 0; e < P.NE; e++)
+      {
+         double J[DIM*DIM*NQ], wd[NQ];
+         VectorGrad(P, x, e, J);
+         for (int q = 0; q < NQ; q++) { wd[q] = P.qweights[q]*sm::Det<DIM>(J + DIM*DIM*q); }
+         std::vector<double> M((size_t)NL*NL), b(NL);
+         for (int i = 0; i < NL; i++)
+         {
+            double r = 0.0;
+            for (int q = 0; q < NQ; q++) { r += rho0DetJ0w[(size_t)e*NQ + q]*phi[(size_t)i*NQ + q]; }
+            b[i] = r;
+            for (int j = 0; j < NL; j++)
+            {
+               double a = 0.0;
+               for (int q = 0; q < NQ; q++) { a += wd[q]*phi[(size_t)i*NQ + q]*phi[(size_t)j*NQ + q]; }
+               M[(size_t)i*NL + j] = a;
+            }
+         }
+         // LU with partial pivoting, in place; then forward / back substitution
+         for (int k = 0; k < NL; k++)
+         {
+            int piv = k;
+            for (int i = k + 1; i < NL; i++) { if (std::fabs(M[(size_t)i*NL + k]) > std::fabs(M[(size_t)piv*NL + k])) { piv = i; } }
+            if (piv != k)
+            {
+               for (int j = 0; j < NL; j++) { std::swap(M[(size_t)k*NL + j], M[(size_t)piv*NL + j]); }
+               std::swap(b[k], b[piv]);
+            }
+            for (int i = k + 1; i < NL; i++)
+            {
+               const double f = M[(size_t)i*NL + k]/M[(size_t)k*NL + k];
+               for (int j = k + 1; j < NL; j++) { M[(size_t)i*NL + j] -= f*M[(size_t)k*NL + j]; }
+               b[i] -= f*b[k];
+            }
+         }
+         for (int i = NL - 1; i >= 0; i--)
+         {
+            double r = b[i];
+            for (int j = i + 1; j < NL; j++) { r -= M[(size_t)i*NL + j]*rho[(size_t)e*NL + j]; }
+            rho[(size_t)e*NL + i] = r/M[(size_t)i*NL + i];
+         }
+      }
+   }
    static double EnergyIntegralH1(const Problem &P, const double *rho0DetJ0w, const double *v)
    {
       const double *B = P.tab.B.data();
@@ -484,6 +541,7 @@ struct KernelTable
    void (*Rho0DetJ0Vol)(const Problem&, const double*, const double*, QuadratureData&, std::vector<double>&, double&) = nullptr;
    double (*QUpdate)(const Problem&, const double*, bool, bool, double, double, QuadratureData&, int, int) = nullptr;
    void (*TaylorSource)(const Problem&, const double*, double*) = nullptr;
+   void (*ComputeDensity)(const Problem&, const double*, const double*, double*) = nullptr;
 };
 
 template<int DIM, int D1D, int Q1D>
@@ -495,6 +553,7 @@ static KernelTable make_table()
    t.EnergyIntegralL2 = &K::EnergyIntegralL2; t.EnergyIntegralH1 = &K::EnergyIntegralH1;
    t.ForceMult = &K::ForceMult; t.ForceMultTranspose = &K::ForceMultTranspose;
    t.Rho0DetJ0Vol = &K::Rho0DetJ0Vol; t.QUpdate = &K::QUpdate; t.TaylorSource = &K::TaylorSource;
+   t.ComputeDensity = &K::ComputeDensity;
    return t;
 }
 
@@ -676,6 +735,7 @@ struct Hydro
    // reference LagrangianHydroOperator::InternalEnergy / KineticEnergy (laghos_solver.cpp:639-697)
    double InternalEnergy(const double *e_gf) const { return K.EnergyIntegralL2(P, qd.rho0DetJ0w.data(), e_gf); }
    double KineticEnergy(const double *v) const { return 0.5*K.EnergyIntegralH1(P, qd.rho0DetJ0w.data(), v); }
+   void ComputeDensity(const double *x, double *rho) const { K.ComputeDensity(P, x, qd.rho0DetJ0w.data(), rho); }
    void EMassMult(const double *x, double *y) const
    {
       for_elements([&](int a, int b) { K.MassL2(P, massD.data(), x, y, a, b); });
@@ -928,6 +988,7 @@ static inline RunResult run(const Problem &P, const RunOptions &opt, std::vector
    auto add = [&](const std::vector<double> &a, double c, const std::vector<double> &b, std::vector<double> &o, int64_t n)
    { for (int64_t i = 0; i < n; i++) { o[i] = a[i] + c*b[i]; } };
 
+   std::vector<std::vector<double>> k6;
    auto Step = [&](std::vector<double> &x, double &tt, double dtt)
    {
       switch (opt.ode_solver_type)
@@ -968,6 +1029,28 @@ static inline RunResult run(const Problem &P, const RunOptions &opt, std::vector
             hydro.Mult(y.data(), k.data());           // k4
             add(z, dtt/6, k, x, N);
             break;
+         case 6: // RK6Solver: MFEM's 8-stage 6th-order Verner scheme through ExplicitRKSolver::Step (laghos.cpp:529)
+         {
+            static const double a6[28] = {.6e-1,
+   .1923996296296296296296296296296296296296e-1, .7669337037037037037037037037037037037037e-1,
+   .35975e-1, 0., .107925,
+   1.318683415233148260919747276431735612861, 0., -5.042058063628562225427761634715637693344, 4.220674648395413964508014358283902080483,
+   -41.87259166432751461803757780644346812905, 0., 159.4325621631374917700365669070346830453, -122.1192135650100309202516203389242140663, 5.531743066200053768252631238332999150076,
+   -54.43015693531650433250642051294142461271, 0., 207.0672513650184644273657173866509835987, -158.6108137845899991828742424365058599469, 6.991816585950242321992597280791793907096, -.1859723106220323397765171799549294623692e-1,
+   -54.66374178728197680241215648050386959351, 0., 207.9528062553893734515824816699834244238, -159.2889574744995071508959805871426654216, 7.018743740796944434698170760964252490817, -.1833878590504572306472782005141738268361e-1, -.5119484997882099077875432497245168395840e-3};
+            static const double b6[8] = {.3438957868357036009278820124728322386520e-1, 0., 0., .2582624555633503404659558098586120858767, .4209371189673537150642551514069801967032,
+   4.405396469669310170148836816197095664891, -176.4831190242986576151740942499002125029, 172.3641334014150730294022582711902413315};
+            if (k6.size() != 8) { k6.assign(8, std::vector<double>(N, 0.0)); }
+            hydro.Mult(x.data(), k6[0].data());
+            for (int l = 0, i = 1; i < 8; i++)
+            {
+               add(x, a6[l++]*dtt, k6[0], y, N);
+               for (int j = 1; j < i; j++) { const double c = a6[l++]*dtt; for (int64_t q = 0; q < N; q++) { y[q] += c*k6[j][q]; } }
+               hydro.Mult(y.data(), k6[i].data());
+            }
+            for (int i = 0; i < 8; i++) { const double c = b6[i]*dtt; for (int64_t q = 0; q < N; q++) { x[q] += c*k6[i][q]; } }
+            break;
+         }
          case 7: // RK2AvgSolver::Step
          {
             S0 = x;
@@ -1024,7 +1107,7 @@ static inline RunResult run(const Problem &P, const RunOptions &opt, std::vector
    res.steps = steps; res.t = t; res.dt = dt;
    res.energy_final = hydro.InternalEnergy(S.data() + 2*NV) + hydro.KineticEnergy(S.data() + NV);
    int stages = 1;
-   switch (opt.ode_solver_type) { case 2: stages = 2; break; case 3: stages = 3; break; case 4: stages = 4; break; case 7: stages = 2; break; }
+   switch (opt.ode_solver_type) { case 2: stages = 2; break; case 3: stages = 3; break; case 4: stages = 4; break; case 6: stages = 8; break; case 7: stages = 2; break; }
    res.stages = stages;
    hydro.FOM((long long)steps*stages, res.fom);
    res.timer = hydro.timer;

@@ -119,6 +119,7 @@ void orc_taylor_source(void *hh, const double *x, double *esrc)
 }
 double orc_internal_energy(void *hh, const double *e) { return ((OrcHandle*)hh)->H->InternalEnergy(e); }
 double orc_kinetic_energy(void *hh, const double *v) { return ((OrcHandle*)hh)->H->KineticEnergy(v); }
+void orc_compute_density(void *hh, const double *x, double *rho) { ((OrcHandle*)hh)->H->ComputeDensity(x, rho); }
 // dS_dt = f(S): one call of LagrangianHydroOperator::Mult with fresh quadrature data
 void orc_mult(void *hh, const double *S, double *dS_dt)
 {

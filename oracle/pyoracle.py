@@ -47,6 +47,7 @@ def load():
         lib.orc_internal_energy.restype = C.c_double
         lib.orc_kinetic_energy.argtypes = [C.c_void_p, dp]
         lib.orc_kinetic_energy.restype = C.c_double
+        lib.orc_compute_density.argtypes = [C.c_void_p, dp, dp]
         lib.orc_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                 C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                 dp, dp, C.c_int, dp]
@@ -155,6 +156,11 @@ class Oracle:
 
     def kinetic_energy(self, v):
         return self.lib.orc_kinetic_energy(self.h, _p(np.ascontiguousarray(v)))
+
+    def compute_density(self, x):
+        rho = np.zeros(self.ndofs_l2)
+        self.lib.orc_compute_density(self.h, _p(np.ascontiguousarray(x)), _p(rho))
+        return rho
 
     def mult(self, S):
         d = np.zeros(self.s_size)

@@ -97,3 +97,17 @@ def test_e2e_host_state_matches_resident(built):
     assert a["steps"] == b["steps"]
     assert abs(a["e_norm"] - b["e_norm"]) <= 1e-11 * abs(a["e_norm"])
     assert b["h2d_bytes_per_step"] > 0 and b["d2h_bytes_per_step"] > 0
+
+
+@pytest.mark.parametrize("ode", [1, 2, 3, 6, 7], ids=["euler", "rk2", "rk3ssp", "rk6", "rk2avg"])
+def test_ode_solver_types_vs_oracle(built, ode):
+    """Every -s value of the reference (laghos.cpp:519-534; 4 = RK4 is covered above, 6 = MFEM's 8-stage RK6):
+    |e| after every step against the oracle's restatement of the same integrator."""
+    from laghos_b200.api import run
+    kw = dict(mesh="cube01_hex", rs=1, problem=1, ok=2, ot=1, max_tsteps=5, t_final=10.0, cg_tol=1e-12,
+              ode_solver_type=ode)
+    ro = pyoracle.run(**kw, nthreads=4)
+    rg = run(**kw, hist_cap=64)
+    assert rg["steps"] == ro["steps"] and len(rg["hist"]) == len(ro["hist"])
+    for (ti_g, e_g), (ti_o, e_o) in zip(rg["hist"], ro["hist"]):
+        assert ti_g == ti_o and abs(e_g - e_o) <= 1e-9 * abs(e_o), (ode, ti_g, e_g, e_o)

@@ -18,15 +18,19 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("pgrid,problem", [((2, 1, 1), 1), ((1, 2, 1), 0)])
-def test_two_gpu_matches_one(built, pgrid, problem):
-    if _ngpu() < 2:
-        pytest.skip("needs 2 GPUs")
+# (2,2,1): edge dofs shared by 4 ranks; (2,2,2): the 26-neighbour single-phase exchange of the 8-GPU
+# weak-scaling run (faces, edges shared by 4 ranks, the centre corner shared by all 8)
+@pytest.mark.parametrize("pgrid,problem", [((2, 1, 1), 1), ((1, 2, 1), 0), ((2, 2, 1), 1), ((2, 2, 2), 1), ((2, 2, 2), 0)],
+                         ids=["2x1x1-sedov", "1x2x1-tg", "2x2x1-sedov", "2x2x2-sedov", "2x2x2-tg"])
+def test_n_gpu_matches_one(built, pgrid, problem):
+    nr = pgrid[0] * pgrid[1] * pgrid[2]
+    if _ngpu() < nr:
+        pytest.skip(f"needs {nr} GPUs")
     from laghos_b200.api import run
     kw = dict(mesh="cube01_hex", rs=2, problem=problem, ok=3, ot=2, max_tsteps=6, t_final=1e9, cg_tol=1e-12)
     ref = run(**kw, hist_cap=1024)
     port = 29600 + os.getpid() % 300
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nr),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_check.py"),
            "--pgrid", ",".join(map(str, pgrid)), "--rs", "2", "--problem", str(problem), "--ok", "3", "--ot", "2",
            "--steps", "6"]

@@ -174,6 +174,20 @@ def test_cg_emass(pair):
         assert relerr(xd.cpu().numpy(), xr) < 1e-6
 
 
+def test_compute_density(pair):
+    """ComputeDensity (reference laghos_solver.cpp:542-563) on the initial and on a moved mesh vs the oracle's
+    dense LU solves; at t = 0 it reproduces the initial density field."""
+    P, O, ctxs = pair
+    if P.L1D < 1:
+        pytest.skip("no thermodynamic dofs")
+    S = perturbed_state(P, 5)
+    for x in (P.S0[:P.h1_vsize].copy(), S[:P.h1_vsize].copy()):
+        ref = O.compute_density(x)
+        c = ctxs[0]
+        rho = c.compute_density(c.dev(x)).cpu().numpy()
+        assert relerr(rho, ref) < (1e-10 if P.L1D <= 4 else 1e-8)
+
+
 def test_taylor_source_2d(pair):
     P, O, ctxs = pair
     if P.dim != 2:
