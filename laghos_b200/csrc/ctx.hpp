@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/laghos_b200.h"
 #include "device/pcg.cuh"
+#include "device/p2p.cuh"
 #include <cuda_runtime.h>
 #include <map>
 #include <string>
@@ -112,7 +113,7 @@ struct Ctx
    // variant, [5] 1 = no programmatic dependent launch, [6] mass path (0 default, 1 legacy atomic, 2 brick v1, 3 brick v2),
    // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil), [8] 1 = first PCG vector kernels (update_xr/update_d),
    // [9] 1 = plain (not fused) PCG on the multi-launch brick kernels, [10] 1 = energy solve by the reference's CG
-   // instead of the element inverses
+   // instead of the element inverses, [11] 1 = NCCL send/recv + all-reduce instead of the peer-memory exchanges
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing
@@ -130,6 +131,13 @@ struct Ctx
    unsigned char *d_pack_nb = nullptr;
    double *d_send_all = nullptr, *d_recv_all = nullptr;
    int64_t ne_global = 0;
+   // NVLink peer-memory exchanges (device/p2p.cuh): every rank's communication buffer mapped through cudaIpc
+   bool p2p_on = false;
+   p2p::Dev p2p_dev;
+   char *p2p_base = nullptr;                        // own buffer (cudaMalloc)
+   std::vector<void*> p2p_opened;                   // peers' mappings (cudaIpcCloseMemHandle on destroy)
+   unsigned long long p2p_scal_seq = 0, p2p_halo_seq = 0;
+   int *d_nbr_roff = nullptr, *d_nbr_rank = nullptr; unsigned int *d_pack_done = nullptr;
 };
 
 // helpers implemented in capi.cu
