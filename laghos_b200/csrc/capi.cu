@@ -14,6 +14,9 @@ static thread_local std::string g_err;
 int64_t g_launch_count = 0;
 void set_error(const std::string &msg) { g_err = msg; }
 
+// CTAs of a PCG finish kernel: a small grid with a last-arrival second stage pays off above a few thousand partials
+static int fin_grid(int npart) { return npart > 4096 ? pcg::FIN_CTAS : 1; }
+
 int vec_grid(int64_t n)
 {
    const int64_t b = (n + pcg::RB - 1)/pcg::RB;
@@ -198,13 +201,12 @@ int halo_sum(Ctx &c, double *v, int nc)
       const unsigned long long seq = ++c.p2p_halo_seq;
       const int nnbr = (int)c.nbrs.size();
       const int g = std::max(1, std::min(296, (c.halo_total + 255)/256));
-      p2p::halo_pack_p2p<<<g, 256, 0, c.stream>>>(c.p2p_dev, seq, c.halo_total, nc, c.ndofs, c.d_pack_idx, c.d_pack_nb, c.d_nbr_off,
-                                                  c.d_nbr_n, c.d_nbr_roff, c.d_nbr_rank, nnbr, v, c.d_pack_done);
-      LAGB_LAUNCH_CHECK();
-      p2p::halo_combine_p2p<<<std::max(1, std::min(296, (c.halo_nu + 255)/256)), 256, 0, c.stream>>>(
-         c.p2p_dev, seq, c.halo_nu, nc, c.ndofs, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n,
-         c.d_nbr_rank, nnbr, v);
-      LAGB_LAUNCH_CHECK();
+      LAGB_LAUNCH_K(c, p2p::halo_pack_p2p, g, 256, 0, c.p2p_dev, seq, c.halo_total, nc, (int64_t)c.ndofs, (const int*)c.d_pack_idx,
+                    (const unsigned char*)c.d_pack_nb, (const int*)c.d_nbr_off, (const int*)c.d_nbr_n, (const int*)c.d_nbr_roff,
+                    (const int*)c.d_nbr_rank, nnbr, (const double*)v, c.d_pack_done);
+      LAGB_LAUNCH_K(c, p2p::halo_combine_p2p, std::max(1, std::min(296, (c.halo_nu + 255)/256)), 256, 0, c.p2p_dev, seq, c.halo_nu, nc,
+                    (int64_t)c.ndofs, (const int*)c.d_u_dof, (const int*)c.d_u_ptr, (const int*)c.d_u_src, (const unsigned char*)c.d_pack_nb,
+                    (const int*)c.d_nbr_off, (const int*)c.d_nbr_n, (const int*)c.d_nbr_rank, nnbr, v);
       return LAGB_OK;
    }
    if (c.halo_single)
@@ -443,6 +445,7 @@ static int p2p_setup(Ctx &c, int nnbr, const int32_t *nbr_rank)
       rc = dev_upload(&c.d_nbr_rank, nr.data(), nr.size()); if (rc) { return rc; }
    }
    { int rc = dev_alloc(&c.d_pack_done, 1); if (rc) { return rc; } LAGB_CUDA(cudaMemset(c.d_pack_done, 0, sizeof(unsigned int))); }
+   { int rc = dev_upload(&c.d_p2p_dev, &c.p2p_dev, 1); if (rc) { return rc; } }
    c.p2p_on = true;
    return LAGB_OK;
 }
@@ -470,9 +473,10 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    const bool zero_z = !l2 && !bapply;   // only the atomic scatter accumulates into z
 
    // apply: z (+)= A v ; returns number of partial blocks if the kernel produced d^t A d partials
+   size_t den_src_off = 0;     // where the operator's d^t A d partials start inside d_part
    auto apply = [&](const double *v, bool want_den, int &den_blocks) -> int
    {
-      den_blocks = 0;
+      den_blocks = 0; den_src_off = 0;
       if (l2) { return ks.mass_l2(c, v, z); }
       if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
       int rc;
@@ -480,25 +484,24 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       else { rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass); }
       if (rc) { return rc; }
       if (c.profile_mass) { int rt = timer_end(c, 4); if (rt) { return rt; } c.mass_launches++; }
-      if (want_den && (ks.tuned_mass || bapply)) { den_blocks = c.dt_nblocks; }
+      if (want_den && (ks.tuned_mass || bapply)) { den_blocks = c.dt_nblocks; den_src_off = bapply ? 0 : c.den_off; }
       return halo_sum(c, z, NC);
    };
    // per-block partials -> (sum over ranks) -> what the finish kernels read.
    // Single rank: the finish kernel reduces the partials itself (fixed order).
    // Multi rank: reduce to NC sums, NCCL all-reduce in-stream, finish reads the NC sums.
-   auto reduced = [&](int nblocks, double *tmp, const double *&src, int &nsrc) -> int
+   // Multi rank, peer memory (device/p2p.cuh): the finish kernel itself publishes its NC sums to every rank and adds
+   // the ranks' values in rank order (pd != nullptr).  Multi rank, NCCL: reduce to NC sums, all-reduce in-stream,
+   // the finish kernel reads the NC sums.
+   const p2p::Dev *pd = nullptr; unsigned long long pseq = 0;
+   auto reduced = [&](int nblocks, double *tmp, const double *&src, int &nsrc, size_t off = 0) -> int
    {
-      if (c.nranks <= 1) { src = c.d_part; nsrc = nblocks; return LAGB_OK; }
+      pd = nullptr; pseq = 0;
+      const double *part = c.d_part + off;
+      if (c.nranks <= 1) { src = part; nsrc = nblocks; return LAGB_OK; }
+      if (c.p2p_on && c.tune[11] == 0) { src = part; nsrc = nblocks; pd = c.d_p2p_dev; pseq = ++c.p2p_scal_seq; return LAGB_OK; }
       src = tmp; nsrc = 1;
-      if (c.p2p_on && c.tune[11] == 0)
-      {
-         // one launch: last-stage reduction + publication to every rank + fixed-rank-order sum
-         p2p::p2p_allreduce<NC><<<1, pcg::FB, 0, c.stream>>>(c.p2p_dev, ++c.p2p_scal_seq, nblocks, c.d_part, tmp);
-         LAGB_LAUNCH_CHECK();
-         return LAGB_OK;
-      }
-      pcg::reduce_final<NC><<<1, pcg::FB, 0, c.stream>>>(nblocks, c.d_part, tmp);
-      LAGB_LAUNCH_CHECK();
+      LAGB_LAUNCH_K(c, pcg::reduce_final<NC>, 1, pcg::FB, 0, nblocks, part, tmp);
       return allreduce_sum(c, tmp, NC);
    };
 
@@ -510,11 +513,9 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       rc = apply(x, false, den_blocks); if (rc) { return rc; }
    }
    else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
-   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, P, own, r, d, c.d_part, iterative_mode ? 1 : 0);
-   LAGB_LAUNCH_CHECK();
+   LAGB_LAUNCH_K(c, pcg::init_residual<NC>, g, pcg::RB, 0, n, cs, b, z, P, own, r, d, c.d_part, iterative_mode ? 1 : 0);
    rc = reduced(g, c.d_tmp, src, nsrc); if (rc) { return rc; }
-   pcg::finish_init<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, rel_tol, 0.0);
-   LAGB_LAUNCH_CHECK();
+   LAGB_LAUNCH_K(c, pcg::finish_init<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, rel_tol, 0.0, pd, pseq, c.d_fin, c.d_grp_ctr);
 
    // The host only needs to know when every component has stopped; iterations are
    // enqueued ahead (kernels skip finished components) and the flag is polled at
@@ -536,35 +537,27 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       rc = apply(d, true, den_blocks); if (rc) { return rc; }
       if (den_blocks == 0)
       {
-         pcg::dot_partial<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, d, z, own, c.d_part);
-         LAGB_LAUNCH_CHECK();
-         den_blocks = g;
+         LAGB_LAUNCH_K(c, pcg::dot_partial<NC>, g, pcg::RB, 0, n, cs, (const double*)d, (const double*)z, own, c.d_part);
+         den_blocks = g; den_src_off = 0;
       }
-      rc = reduced(den_blocks, c.d_tmp, src, nsrc); if (rc) { return rc; }
-      pcg::finish_den<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it);
-      LAGB_LAUNCH_CHECK();
+      rc = reduced(den_blocks, c.d_tmp, src, nsrc, den_src_off); if (rc) { return rc; }
+      LAGB_LAUNCH_K(c, pcg::finish_den<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, it, pd, pseq, c.d_fin, c.d_grp_ctr);
       if (c.tune[8] == 1)
       {
          // first version: x and r in one kernel, d (and the zero fill of z) in another
-         pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, d, z, P, own, c.d_part);
-         LAGB_LAUNCH_CHECK();
+         LAGB_LAUNCH_K(c, pcg::update_xr<NC>, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, x, r, (const double*)d, (const double*)z, P, own, c.d_part);
          rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
-         pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
-         LAGB_LAUNCH_CHECK();
-         pcg::update_d<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, d, r, P, z);
-         LAGB_LAUNCH_CHECK();
+         LAGB_LAUNCH_K(c, pcg::finish_beta<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, it, max_iter, pd, pseq, c.d_fin, c.d_grp_ctr);
+         LAGB_LAUNCH_K(c, pcg::update_d<NC>, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, d, (const double*)r, P, z);
       }
       else
       {
          // same arithmetic, one vector pass less: x is updated where d is read anyway
-         pcg::update_r<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, r, z, P, own, c.d_part);
-         LAGB_LAUNCH_CHECK();
+         LAGB_LAUNCH_K(c, pcg::update_r<NC>, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, r, (const double*)z, P, own, c.d_part);
          rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
-         pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
-         LAGB_LAUNCH_CHECK();
-         if (zero_z) { pcg::update_dx<NC,true><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, d, r, P, z); }
-         else { pcg::update_dx<NC,false><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, d, r, P, z); }
-         LAGB_LAUNCH_CHECK();
+         LAGB_LAUNCH_K(c, pcg::finish_beta<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, it, max_iter, pd, pseq, c.d_fin, c.d_grp_ctr);
+         auto kz = pcg::update_dx<NC,true>; auto kn = pcg::update_dx<NC,false>;
+         LAGB_LAUNCH_K(c, zero_z ? kz : kn, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, x, d, (const double*)r, P, z);
       }
       if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
    }
@@ -622,7 +615,7 @@ static int pcg_run_brick(Ctx &c, int comp0, const double *b, double *x, double r
    pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, P, own, r, dcur, c.d_part, iterative_mode ? 1 : 0);
    LAGB_LAUNCH_CHECK();
    rc = reduced(g, c.d_tmp, src, nsrc); if (rc) { return rc; }
-   pcg::finish_init<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, rel_tol, 0.0);   // beta = 0: first direction = M^-1 r
+   pcg::finish_init<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, rel_tol, 0.0, nullptr, 0ull, c.d_fin, c.d_grp_ctr);   // beta = 0: first direction = M^-1 r
    LAGB_LAUNCH_CHECK();
 
    int next_check = std::max(1, c.predicted_iters - 1);
@@ -642,12 +635,12 @@ static int pcg_run_brick(Ctx &c, int comp0, const double *b, double *x, double r
       MassBrickIn in; in.r = r; in.dold = dcur; in.dnew = dnxt; in.comp0 = comp0;
       rc = apply(in, true); if (rc) { return rc; }
       rc = reduced(c.dt_nblocks, c.d_tmp, src, nsrc); if (rc) { return rc; }
-      pcg::finish_den<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it);
+      pcg::finish_den<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, nullptr, 0ull, c.d_fin, c.d_grp_ctr);
       LAGB_LAUNCH_CHECK();
       pcg::update_xr<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, c.d_state, x, r, dnxt, z, P, own, c.d_part);
       LAGB_LAUNCH_CHECK();
       rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
-      pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter);
+      pcg::finish_beta<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, it, max_iter, nullptr, 0ull, c.d_fin, c.d_grp_ctr);
       LAGB_LAUNCH_CHECK();
       std::swap(dcur, dnxt);
       if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
@@ -763,6 +756,10 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    rc |= dev_alloc(&c.d_lz, (size_t)c.ndofs_l2);
    c.part_cap = std::max(c.NE, 148*16)*4 + 64;
    rc |= dev_alloc(&c.d_part, (size_t)c.part_cap);
+   c.grp_cap = 64;
+   rc |= dev_alloc(&c.d_grp_ctr, (size_t)c.grp_cap);
+   rc |= dev_alloc(&c.d_fin, (size_t)pcg::FIN_CTAS*pcg::MAXC);
+   if (!rc) { rc |= (cudaMemset(c.d_grp_ctr, 0, sizeof(unsigned int)*(size_t)c.grp_cap) != cudaSuccess); }
    rc |= dev_alloc(&c.d_tmp, 16); rc |= dev_alloc(&c.d_dt, 1); rc |= dev_alloc(&c.d_elem_vol, (size_t)c.NE);
    rc |= dev_alloc(&c.d_state, 1);
    if (rc) { lagb_ctx_destroy(h); return LAGB_ERR_CUDA; }
@@ -779,6 +776,18 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    };
    rc = finish();
    if (rc) { lagb_ctx_destroy(h); return rc; }
+   // measurement aid: LAGB_TUNE="key=value,key=value" presets lagb_tune_set for contexts created by drivers that
+   // do not expose the knobs (bench.py A/B runs)
+   if (const char *tv = getenv("LAGB_TUNE"))
+   {
+      int k = 0, v = 0, used = 0;
+      while (sscanf(tv, " %d=%d%n", &k, &v, &used) == 2)
+      {
+         if (k >= 0 && k < 16) { c.tune[k] = v; }
+         tv += used;
+         if (*tv == ',') { tv++; }
+      }
+   }
    *out = h;
    return LAGB_OK;
 }
@@ -790,7 +799,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    cudaStreamSynchronize(c.stream);
    void *ptrs[] = {c.d_map, c.d_ess[0], c.d_ess[1], c.d_ess[2], c.d_qweights, c.d_inv_qweights, c.d_gamma, c.d_sJit, c.d_rho0DetJ0w,
                    c.d_Jac0inv, c.d_massD, c.d_diag, c.d_dinv, c.d_essmask, c.d_r, c.d_d, c.d_z, c.d_lr, c.d_ld, c.d_lz,
-                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own, c.d_d2, c.d_l2inv, c.d_BL};
+                   c.d_part, c.d_tmp, c.d_dt, c.d_elem_vol, c.d_state, c.d_own, c.d_d2, c.d_l2inv, c.d_BL, c.d_grp_ctr, c.d_fin};
    for (void *p : ptrs) { if (p) { cudaFree(p); } }
    for (auto &kv : c.plans)
    {
@@ -809,7 +818,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (int w = 0; w < Timer::NT; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
    for (auto e : c.timer.pool) { cudaEventDestroy(e); }
    for (void *p : c.p2p_opened) { cudaIpcCloseMemHandle(p); }
-   { void *pp[] = {c.p2p_base, c.d_nbr_roff, c.d_nbr_rank, c.d_pack_done}; for (void *p : pp) { if (p) { cudaFree(p); } } }
+   { void *pp[] = {c.p2p_base, c.d_nbr_roff, c.d_nbr_rank, c.d_pack_done, c.d_p2p_dev}; for (void *p : pp) { if (p) { cudaFree(p); } } }
    if (c.nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c.nccl_comm); }
    delete h;
 }

@@ -20,6 +20,24 @@ extern int64_t g_launch_count;
 
 struct Ctx;
 
+// Kernel launch with (pdl = true) or without the programmatic-stream-serialisation attribute: the kernel may be
+// scheduled while its predecessor in the stream drains; it calls pdl_wait() (device/common.cuh) before its first
+// dependent access.
+template<typename... KArgs, typename... Args>
+inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+   cudaLaunchAttribute at[1];
+   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+   at[0].val.programmaticStreamSerializationAllowed = 1;
+   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define LAGB_LAUNCH_K(c, kern, grid, block, smem, ...) do { lagb::g_launch_count++; \
+   cudaError_t err__ = lagb::launch_k((c).tune[12] == 0, kern, dim3(grid), dim3(block), smem, (c).stream, __VA_ARGS__); \
+   if (err__ != cudaSuccess) { lagb::set_error(std::string("kernel launch: ") + cudaGetErrorString(err__)); return LAGB_ERR_CUDA; } } while (0)
+
 // input of the brick mass apply (device/mass3d_brick.cuh): plain x, or the fused PCG direction
 // update d_new = M^-1 r + beta d_old (x == nullptr)
 struct MassBrickIn
@@ -99,6 +117,8 @@ struct Ctx
    // element inverses of the L2 mass matrix (device/l2solve.cuh), built on the first energy solve
    double *d_l2inv = nullptr, *d_BL = nullptr; int l2inv_state = 0;   // 0 not tried, 1 ready, -1 unavailable (memory)
    double *d_part = nullptr; int part_cap = 0;                 // reduction partials
+   unsigned int *d_grp_ctr = nullptr; int grp_cap = 0; size_t den_off = 0;   // arrival ticket of the multi-CTA finish kernels
+   double *d_fin = nullptr;                                    // their per-CTA chunk sums
    double *d_tmp = nullptr;                                    // [8] reduced scalars
    double *d_dt = nullptr;                                     // [1]
    double *d_elem_vol = nullptr;
@@ -113,7 +133,8 @@ struct Ctx
    // variant, [5] 1 = no programmatic dependent launch, [6] mass path (0 default, 1 legacy atomic, 2 brick v1, 3 brick v2),
    // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil), [8] 1 = first PCG vector kernels (update_xr/update_d),
    // [9] 1 = plain (not fused) PCG on the multi-launch brick kernels, [10] 1 = energy solve by the reference's CG
-   // instead of the element inverses, [11] 1 = NCCL send/recv + all-reduce instead of the peer-memory exchanges
+   // instead of the element inverses, [11] 1 = NCCL send/recv + all-reduce instead of the peer-memory exchanges,
+   // [12] 1 = plain launches (no programmatic dependent launch) in the PCG iteration
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing
@@ -133,7 +154,7 @@ struct Ctx
    int64_t ne_global = 0;
    // NVLink peer-memory exchanges (device/p2p.cuh): every rank's communication buffer mapped through cudaIpc
    bool p2p_on = false;
-   p2p::Dev p2p_dev;
+   p2p::Dev p2p_dev; p2p::Dev *d_p2p_dev = nullptr;  // host copy (kernel parameter) and device copy (finish kernels)
    char *p2p_base = nullptr;                        // own buffer (cudaMalloc)
    std::vector<void*> p2p_opened;                   // peers' mappings (cudaIpcCloseMemHandle on destroy)
    unsigned long long p2p_scal_seq = 0, p2p_halo_seq = 0;

@@ -52,6 +52,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
        const double *__restrict__ x, double *__restrict__ y, double *__restrict__ den_part)
 {
    using C = Mass3DCfg<D1D,Q1D,NB,NC>;
+   pdl_launch();                    // the PCG's next kernel may be staged while this grid drains
    extern __shared__ double sV[];   // [c][e_loc][dz][PLANE]
    int *sIdx = reinterpret_cast<int*>(sV + C::SMEM_DOUBLES);   // [e_loc][dz][IDXS]
    const int t = threadIdx.x;
@@ -77,6 +78,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
          for (int qz = 0; qz < Q1D; qz++) { dq[k][qz] = __ldg(dptr + C::QQ*qz); }
       }
    }
+   pdl_wait();                      // x (and the zero-filled y) come from the predecessor kernel; D and the map do not
    // ---- phase 0: cooperative gather, lanes along the element-local dof index (runs of D1D
    //      contiguous L-vector entries per lattice row).  Slice (c,e,dz) is parked in the
    //      first DD slots of its own plane.

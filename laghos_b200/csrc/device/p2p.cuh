@@ -20,55 +20,10 @@
 // Spin loops give up after ~2^28 polls and set an error word instead of hanging the device.
 #pragma once
 #include "pcg.cuh"
+#include "p2p_prims.cuh"
 
 namespace lagb {
 namespace p2p {
-
-constexpr int MAXR = 64;          // ranks
-constexpr int SLOTW = 4;          // doubles per (parity, rank) scalar slot
-
-struct Layout                     // byte offsets inside every rank's communication buffer
-{
-   size_t scal, sflag, hflag, halo[2], err;
-   size_t bytes;
-};
-struct Dev                        // passed by value to the kernels
-{
-   char *peer[MAXR];              // mapped base address of every rank's buffer (peer[rank] = own)
-   int rank, nranks;
-   Layout lay;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-   unsigned long long v;
-   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-   return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double *p, double v)
-{
-   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double *p)
-{
-   double v;
-   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-   return v;
-}
-__device__ __forceinline__ bool wait_flag(const unsigned long long *p, unsigned long long seq, char *own_base, const Layout &lay)
-{
-   for (unsigned int it = 0; it < (1u << 28); it++)
-   {
-      if (ld_acquire_sys(p) >= seq) { return true; }
-      if (it > 64) { __nanosleep(40); }
-   }
-   *reinterpret_cast<volatile int*>(own_base + lay.err) = 1;
-   return false;
-}
 
 // out[c] = sum over ranks (ascending) of sum_b part[b*NC + c]
 template<int NC>
@@ -76,33 +31,13 @@ __global__ void __launch_bounds__(pcg::FB)
 p2p_allreduce(const Dev d, const unsigned long long seq, const int nblocks, const double *__restrict__ part,
               double *__restrict__ out)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
    __shared__ double mine[NC];
    double tmp[NC];
    pcg::reduce_to_thread0<NC>(part, nblocks, tmp, sh);
-   if (threadIdx.x == 0) { for (int c = 0; c < NC; c++) { mine[c] = tmp[c]; } }
-   __syncthreads();
-   const int par = (int)(seq & 1ull);
-   const int t = threadIdx.x;
-   if (t < d.nranks)
-   {
-      // publish into rank t's slot [par][my rank]
-      double *slot = reinterpret_cast<double*>(d.peer[t] + d.lay.scal) + ((size_t)par*d.nranks + d.rank)*SLOTW;
-      for (int c = 0; c < NC; c++) { st_relaxed_sys(slot + c, mine[c]); }
-      __threadfence_system();
-      st_release_sys(reinterpret_cast<unsigned long long*>(d.peer[t] + d.lay.sflag) + (size_t)par*d.nranks + d.rank, seq);
-      // wait for rank t's publication in my own buffer
-      wait_flag(reinterpret_cast<const unsigned long long*>(d.peer[d.rank] + d.lay.sflag) + (size_t)par*d.nranks + t, seq,
-                d.peer[d.rank], d.lay);
-   }
-   __syncthreads();
-   if (t < NC)
-   {
-      const double *slots = reinterpret_cast<const double*>(d.peer[d.rank] + d.lay.scal) + (size_t)par*d.nranks*SLOTW;
-      double s = 0.0;
-      for (int r = 0; r < d.nranks; r++) { s += ld_relaxed_sys(slots + (size_t)r*SLOTW + t); }
-      out[t] = s;
-   }
+   allreduce_cta<NC>(d, seq, tmp, mine);
+   if (threadIdx.x == 0) { for (int c = 0; c < NC; c++) { out[c] = tmp[c]; } }
 }
 
 // pack every (neighbour, shared dof) entry into the neighbour's receive area; message layout per neighbour k:
@@ -113,6 +48,7 @@ static __global__ void halo_pack_p2p(const Dev d, const unsigned long long seq, 
                               const int *__restrict__ nbr_rank, int nnbr, const double *__restrict__ v,
                               unsigned int *__restrict__ done)
 {
+   pdl_launch(); pdl_wait();
    const int par = (int)(seq & 1ull);
    for (int J = blockIdx.x*blockDim.x + threadIdx.x; J < total; J += gridDim.x*blockDim.x)
    {
@@ -143,6 +79,7 @@ static __global__ void halo_combine_p2p(const Dev d, const unsigned long long se
                                  const unsigned char *__restrict__ nbk, const int *__restrict__ off, const int *__restrict__ cnt,
                                  const int *__restrict__ nbr_rank, int nnbr, double *__restrict__ v)
 {
+   pdl_launch(); pdl_wait();
    const int par = (int)(seq & 1ull);
    for (int k = threadIdx.x; k < nnbr; k += blockDim.x)
    {

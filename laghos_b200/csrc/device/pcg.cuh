@@ -14,6 +14,7 @@
 // All reductions are two-stage with fixed summation order (deterministic).
 #pragma once
 #include "common.cuh"
+#include "p2p_prims.cuh"
 
 namespace lagb {
 namespace pcg {
@@ -64,6 +65,7 @@ __global__ void init_residual(int64_t n, int64_t cstride, const double *__restri
                               double *__restrict__ r, double *__restrict__ d, double *__restrict__ part,
                               int iterative_mode)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
    double acc[NC];
 #pragma unroll
@@ -94,6 +96,7 @@ template<int NC>
 __global__ void dot_partial(int64_t n, int64_t cstride, const double *__restrict__ x, const double *__restrict__ y,
                             const unsigned char *__restrict__ own, double *__restrict__ part)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
    double acc[NC];
 #pragma unroll
@@ -116,6 +119,7 @@ __global__ void dot_partial(int64_t n, int64_t cstride, const double *__restrict
 template<int NC>
 __global__ void reduce_partials(int nblocks, const double *__restrict__ part, double *__restrict__ out)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
 #pragma unroll
    for (int c = 0; c < NC; c++)
@@ -161,10 +165,50 @@ __device__ __forceinline__ void reduce_to_thread0(const double *__restrict__ par
    }
 }
 
+// The same over a small grid: CTA b reduces the b-th contiguous chunk (fixed order), the last CTA to arrive
+// (atomic ticket) adds the chunk sums in CTA order.  A single CTA needs ~17 us for the 98304 partials of the
+// mass kernel at 64^3 elements (pure load latency); 32 CTAs need ~4 us.  Returns true on the CTA that holds the
+// total (valid on its thread 0); deterministic.
+constexpr int FIN_CTAS = 32;
+template<int NC>
+__device__ __forceinline__ bool reduce_grid(const double *__restrict__ part, int nblocks, double *stage, unsigned int *ctr,
+                                            double *out, double *sh)
+{
+   if (gridDim.x == 1) { reduce_to_thread0<NC>(part, nblocks, out, sh); return true; }
+   const int per = (nblocks + gridDim.x - 1)/gridDim.x;
+   const int b0 = min(nblocks, (int)blockIdx.x*per), b1 = min(nblocks, b0 + per);
+   reduce_to_thread0<NC>(part + (size_t)b0*NC, b1 - b0, out, sh);
+   __shared__ bool last;
+   __shared__ double chunk[FIN_CTAS*MAXC];
+   if (threadIdx.x == 0)
+   {
+      for (int c = 0; c < NC; c++) { stage[blockIdx.x*NC + c] = out[c]; }
+      __threadfence();
+      last = (atomicAdd(ctr, 1u) == gridDim.x - 1);
+   }
+   __syncthreads();
+   if (!last) { return false; }
+   __threadfence();
+   if (threadIdx.x < gridDim.x*NC) { chunk[threadIdx.x] = __ldcg(stage + threadIdx.x); }
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {
+      for (int c = 0; c < NC; c++)
+      {
+         double s = 0.0;
+         for (unsigned int b = 0; b < gridDim.x; b++) { s += chunk[b*NC + c]; }
+         out[c] = s;
+      }
+      *ctr = 0u;
+   }
+   return true;
+}
+
 // multi-rank path: partials -> NC sums (input of the NCCL all-reduce)
 template<int NC>
-__global__ void reduce_final(int nblocks, const double *__restrict__ part, double *__restrict__ out)
+__global__ void __launch_bounds__(FB) reduce_final(int nblocks, const double *__restrict__ part, double *__restrict__ out)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
    double tmp[NC];
    reduce_to_thread0<NC>(part, nblocks, tmp, sh);
@@ -174,11 +218,15 @@ __global__ void reduce_final(int nblocks, const double *__restrict__ part, doubl
 // The finish kernels take the per-block partials straight from the producing kernel
 // (nblocks > 1, single rank) or the already reduced and all-reduced sums (nblocks == 1).
 template<int NC>
-__global__ void finish_init(State *st, const double *part, int nblocks, double rel_tol, double abs_tol)
+__global__ void __launch_bounds__(FB) finish_init(State *st, const double *part, int nblocks, double rel_tol, double abs_tol,
+                            const p2p::Dev *pd, unsigned long long seq, double *stage, unsigned int *ctr)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
+   __shared__ double shx[MAXC];
    double tmp[NC];
-   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (!reduce_grid<NC>(part, nblocks, stage, ctr, tmp, sh)) { return; }
+   if (pd) { p2p::allreduce_cta<NC>(*pd, seq, tmp, shx); }
    if (threadIdx.x != 0) { return; }
    int all = 1;
    for (int c = 0; c < NC; c++)
@@ -199,11 +247,15 @@ __global__ void finish_init(State *st, const double *part, int nblocks, double r
 
 // den reduced into tmp: alpha = nom/den
 template<int NC>
-__global__ void finish_den(State *st, const double *part, int nblocks, int iter)
+__global__ void __launch_bounds__(FB) finish_den(State *st, const double *part, int nblocks, int iter,
+                           const p2p::Dev *pd, unsigned long long seq, double *stage, unsigned int *ctr)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
+   __shared__ double shx[MAXC];
    double tmp[NC];
-   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (!reduce_grid<NC>(part, nblocks, stage, ctr, tmp, sh)) { return; }
+   if (pd) { p2p::allreduce_cta<NC>(*pd, seq, tmp, shx); }
    if (threadIdx.x != 0) { return; }
    for (int c = 0; c < NC; c++)
    {
@@ -231,6 +283,7 @@ update_xr(int64_t n, int64_t cstride, const State *__restrict__ st,
           const double *__restrict__ z, const Prec P,
           const unsigned char *__restrict__ own, double *__restrict__ part)
 {
+   pdl_launch(); pdl_wait();
    constexpr int UNR = 2;
    __shared__ double sh[32];
    double acc[NC], alpha[NC];
@@ -286,11 +339,15 @@ update_xr(int64_t n, int64_t cstride, const State *__restrict__ st,
 
 // betanom reduced into tmp: convergence test, beta, nom <- betanom
 template<int NC>
-__global__ void finish_beta(State *st, const double *part, int nblocks, int iter, int max_iter)
+__global__ void __launch_bounds__(FB) finish_beta(State *st, const double *part, int nblocks, int iter, int max_iter,
+                            const p2p::Dev *pd, unsigned long long seq, double *stage, unsigned int *ctr)
 {
+   pdl_launch(); pdl_wait();
    __shared__ double sh[32];
+   __shared__ double shx[MAXC];
    double tmp[NC];
-   reduce_to_thread0<NC>(part, nblocks, tmp, sh);
+   if (!reduce_grid<NC>(part, nblocks, stage, ctr, tmp, sh)) { return; }
+   if (pd) { p2p::allreduce_cta<NC>(*pd, seq, tmp, shx); }
    if (threadIdx.x != 0) { return; }
    int all = 1;
    for (int c = 0; c < NC; c++)
@@ -319,6 +376,7 @@ update_d(int64_t n, int64_t cstride, const State *__restrict__ st,
          double *__restrict__ d, const double *__restrict__ r,
          const Prec P, double *__restrict__ z)
 {
+   pdl_launch(); pdl_wait();
    constexpr int UNR = 2;
    double beta[NC]; bool skip[NC];
 #pragma unroll
@@ -373,6 +431,7 @@ update_r(int64_t n, int64_t cstride, const State *__restrict__ st,
          double *__restrict__ r, const double *__restrict__ z, const Prec P,
          const unsigned char *__restrict__ own, double *__restrict__ part)
 {
+   pdl_launch(); pdl_wait();
    constexpr int UNR = 4;
    __shared__ double sh[32];
    double acc[NC], alpha[NC];
@@ -429,6 +488,7 @@ update_dx(int64_t n, int64_t cstride, const State *__restrict__ st,
           double *__restrict__ x, double *__restrict__ d, const double *__restrict__ r,
           const Prec P, double *__restrict__ z)
 {
+   pdl_launch(); pdl_wait();
    constexpr int UNR = 2;
    double alpha[NC], beta[NC]; bool skip[NC];
 #pragma unroll

@@ -101,16 +101,17 @@ __device__ __forceinline__ void l2_values(const double *BL, int nel, const doubl
                                           double *t1, int s1, double *t2, int s2, double *Eq, int sQ,
                                           int tid, int nthr)
 {
-   constexpr int QQ = Q1D*Q1D, LL = L1D*L1D;
+   // rows of Es and t1 are padded to odd strides (LP, QP): lanes along the row index hit distinct banks
+   constexpr int QQ = Q1D*Q1D, LL = L1D*L1D, QP = Q1D | 1, LP = L1D | 1;
    for (int it = tid; it < nel*LL; it += nthr)            // x pencils (lz, ly)
    {
       const int e = it / LL, r = it - e*LL;
       double in[L1D], out[Q1D];
 #pragma unroll
-      for (int l = 0; l < L1D; l++) { in[l] = Es[e*sE + l + L1D*r]; }
+      for (int l = 0; l < L1D; l++) { in[l] = Es[e*sE + l + LP*r]; }
       pencil_fwd<L1D,Q1D>(BL, in, out);
 #pragma unroll
-      for (int q = 0; q < Q1D; q++) { t1[e*s1 + q + Q1D*r] = out[q]; }     // [lz][ly][qx]
+      for (int q = 0; q < Q1D; q++) { t1[e*s1 + q + QP*r] = out[q]; }     // [lz][ly][qx]
    }
    __syncthreads();
    for (int it = tid; it < nel*L1D*Q1D; it += nthr)       // y pencils (lz, qx)
@@ -119,7 +120,7 @@ __device__ __forceinline__ void l2_values(const double *BL, int nel, const doubl
       const int qx = r % Q1D, lz = r / Q1D;
       double in[L1D], out[Q1D];
 #pragma unroll
-      for (int l = 0; l < L1D; l++) { in[l] = t1[e*s1 + qx + Q1D*(l + L1D*lz)]; }
+      for (int l = 0; l < L1D; l++) { in[l] = t1[e*s1 + qx + QP*(l + L1D*lz)]; }
       pencil_fwd<L1D,Q1D>(BL, in, out);
 #pragma unroll
       for (int q = 0; q < Q1D; q++) { t2[e*s2 + qx + Q1D*(q + Q1D*lz)] = out[q]; }   // [lz][qy][qx]
@@ -143,7 +144,7 @@ template<int L1D, int Q1D>
 __device__ __forceinline__ void l2_values_t_yx(const double *BL, int nel, const double *t2, int s2,
                                                double *t1, int s1, double *out, int tid, int nthr)
 {
-   constexpr int LL = L1D*L1D, NL = LL*L1D;
+   constexpr int LL = L1D*L1D, NL = LL*L1D, QP = Q1D | 1;
    for (int it = tid; it < nel*L1D*Q1D; it += nthr)       // y pencils (lz, qx)
    {
       const int e = it / (L1D*Q1D), r = it - e*(L1D*Q1D);
@@ -153,7 +154,7 @@ __device__ __forceinline__ void l2_values_t_yx(const double *BL, int nel, const 
       for (int q = 0; q < Q1D; q++) { in[q] = t2[e*s2 + qx + Q1D*(q + Q1D*lz)]; }
       pencil_bwd<L1D,Q1D>(BL, in, o);
 #pragma unroll
-      for (int l = 0; l < L1D; l++) { t1[e*s1 + qx + Q1D*(l + L1D*lz)] = o[l]; }   // [lz][ly][qx]
+      for (int l = 0; l < L1D; l++) { t1[e*s1 + qx + QP*(l + L1D*lz)] = o[l]; }   // [lz][ly][qx], rows padded to QP
    }
    __syncthreads();
    for (int it = tid; it < nel*LL; it += nthr)            // x pencils (lz, ly)
@@ -161,7 +162,7 @@ __device__ __forceinline__ void l2_values_t_yx(const double *BL, int nel, const 
       const int e = it / LL, r = it - e*LL;
       double in[Q1D], o[L1D];
 #pragma unroll
-      for (int q = 0; q < Q1D; q++) { in[q] = t1[e*s1 + q + Q1D*r]; }
+      for (int q = 0; q < Q1D; q++) { in[q] = t1[e*s1 + q + QP*r]; }
       pencil_bwd<L1D,Q1D>(BL, in, o);
 #pragma unroll
       for (int l = 0; l < L1D; l++) { out[(size_t)e*NL + l + L1D*r] = o[l]; }
@@ -177,17 +178,18 @@ __device__ __forceinline__ void grad_xy(const double *B, const double *G, int ne
                                         double *Bx, double *Gx, int s1, double *BB, double *GB, double *BG, int s2,
                                         int tid, int nthr)
 {
-   constexpr int DD = D1D*D1D, QQ = Q1D*Q1D;
+   // rows of Xs and Bx/Gx padded to odd strides (DP, QP): no bank conflicts with lanes along the row index
+   constexpr int DD = D1D*D1D, QQ = Q1D*Q1D, QP = Q1D | 1, DP = D1D | 1;
    for (int it = tid; it < nel*NF*DD; it += nthr)         // x pencils (f, dz, dy)
    {
       const int e = it / (NF*DD), r = it - e*(NF*DD);     // r = dy + D*(dz + D*f)
       double in[D1D], b[Q1D], g[Q1D];
 #pragma unroll
-      for (int d = 0; d < D1D; d++) { in[d] = Xs[e*sX + d + D1D*r]; }
+      for (int d = 0; d < D1D; d++) { in[d] = Xs[e*sX + d + DP*r]; }
       pencil_fwd<D1D,Q1D>(B, in, b);
       pencil_fwd<D1D,Q1D>(G, in, g);
 #pragma unroll
-      for (int q = 0; q < Q1D; q++) { Bx[e*s1 + q + Q1D*r] = b[q]; Gx[e*s1 + q + Q1D*r] = g[q]; }
+      for (int q = 0; q < Q1D; q++) { Bx[e*s1 + q + QP*r] = b[q]; Gx[e*s1 + q + QP*r] = g[q]; }
    }
    __syncthreads();
    for (int it = tid; it < nel*NF*D1D*Q1D; it += nthr)    // y pencils (f, dz, qx)
@@ -198,8 +200,8 @@ __device__ __forceinline__ void grad_xy(const double *B, const double *G, int ne
 #pragma unroll
       for (int d = 0; d < D1D; d++)
       {
-         xb[d] = Bx[e*s1 + qx + Q1D*(d + D1D*fz)];
-         xg[d] = Gx[e*s1 + qx + Q1D*(d + D1D*fz)];
+         xb[d] = Bx[e*s1 + qx + QP*(d + D1D*fz)];
+         xg[d] = Gx[e*s1 + qx + QP*(d + D1D*fz)];
       }
       pencil_fwd<D1D,Q1D>(B, xb, bb);
       pencil_fwd<D1D,Q1D>(B, xg, gb);
@@ -222,16 +224,18 @@ struct QUpd3DCfg
 {
    static constexpr int L1D = D1D - 1, DD = D1D*D1D, QQ = Q1D*Q1D, ND = D1D*DD, NQ = Q1D*QQ, NL = L1D*L1D*L1D;
    static constexpr int NF = 6;
-   static constexpr int S_ST1 = NF*DD*Q1D;                 // each of Bx, Gx
+   static constexpr int QP = Q1D | 1, DP = D1D | 1, LP = L1D | 1;   // odd row strides (bank-conflict free pencils)
+   static constexpr int S_ST1 = NF*DD*QP;                  // each of Bx, Gx
    static constexpr int S_ST2 = NF*D1D*QQ;                 // each of BB, GB, BG
-   static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
-   static constexpr int S_DOF = NF*ND + NL;
+   static constexpr int S_E1 = L1D*L1D*QP, S_E2 = L1D*QQ;
+   static constexpr int S_DOF = NF*DD*DP + L1D*L1D*LP;
    // dofs alias the stage-2 arrays (dead after the x pencils)
    static constexpr int S_A = (3*S_ST2 > S_DOF) ? 3*S_ST2 : S_DOF;
    static constexpr int S_TAB = 2*Q1D*D1D + Q1D*L1D;       // B, G, BL for the per-point z pass (runtime qz)
    // the element's Jac0inv (9 NQ) and rho0DetJ0w (NQ) slabs, brought in by bulk asynchronous copies under
    // the gather and the pencil stages; both are 16-byte multiples when NQ is even
-   static constexpr bool BULK = (NQ % 2 == 0);
+   // (up to Q1D = 8: at Q1D = 10 the 80 KB slab would leave one resident CTA per SM)
+   static constexpr bool BULK = (NQ % 2 == 0) && (NQ <= 512);
    static constexpr int S_SLAB = BULK ? 10*NQ : 0;
    static constexpr int SMEM_DOUBLES = S_A + 2*S_ST1 + S_E1 + S_E2 + 32 + S_TAB + S_SLAB + 2;
    static constexpr size_t SMEM_BYTES = sizeof(double)*SMEM_DOUBLES;
@@ -279,17 +283,18 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
       for (int it = tid; it < C::NF*C::ND; it += NT)
       {
          const int i = it % C::ND, f = it / C::ND;
-         A[it] = S[(size_t)f*ndofs + __ldg(m + i)];
+         A[i % D1D + C::DP*(i / D1D + C::DD*f)] = S[(size_t)f*ndofs + __ldg(m + i)];
       }
-      for (int it = tid; it < C::NL; it += NT) { A[C::NF*C::ND + it] = en[(size_t)e*C::NL + it]; }
+      for (int it = tid; it < C::NL; it += NT)
+      { A[C::NF*C::DD*C::DP + it % C::L1D + C::LP*(it / C::L1D)] = en[(size_t)e*C::NL + it]; }
    }
    __syncthreads();
    // Two merged pencil stages (H1 gradient of the 6 fields + L2 interpolation of e) instead of five:
    // every barrier of a one-element CTA costs the latency tail of its slowest warp.
    double *BB = A, *GB = A + C::S_ST2, *BG = A + 2*C::S_ST2;
    {
-      constexpr int DD = C::DD, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D;
-      const double *Es = A + C::NF*C::ND;
+      constexpr int DD = C::DD, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D, QP = C::QP, DP = C::DP, LP = C::LP;
+      const double *Es = A + C::NF*DD*DP;
       // stage alpha: x pencils
       constexpr int nGa = C::NF*DD, nLa = LL;
       for (int it = tid; it < nGa + nLa; it += NT)
@@ -298,21 +303,21 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
          {
             double in[D1D], bo[Q1D], go[Q1D];
 #pragma unroll
-            for (int d = 0; d < D1D; d++) { in[d] = A[d + D1D*it]; }
+            for (int d = 0; d < D1D; d++) { in[d] = A[d + DP*it]; }
             pencil_fwd<D1D,Q1D>(tab.B, in, bo);
             pencil_fwd<D1D,Q1D>(tab.G, in, go);
 #pragma unroll
-            for (int q = 0; q < Q1D; q++) { Bx[q + Q1D*it] = bo[q]; Gx[q + Q1D*it] = go[q]; }
+            for (int q = 0; q < Q1D; q++) { Bx[q + QP*it] = bo[q]; Gx[q + QP*it] = go[q]; }
          }
          else
          {
             const int r = it - nGa;                   // ly + L1D*lz
             double in[L1D], out[Q1D];
 #pragma unroll
-            for (int l = 0; l < L1D; l++) { in[l] = Es[l + L1D*r]; }
+            for (int l = 0; l < L1D; l++) { in[l] = Es[l + LP*r]; }
             pencil_fwd<L1D,Q1D>(tab.BL, in, out);
 #pragma unroll
-            for (int q = 0; q < Q1D; q++) { E1[q + Q1D*r] = out[q]; }   // [lz][ly][qx]
+            for (int q = 0; q < Q1D; q++) { E1[q + QP*r] = out[q]; }   // [lz][ly][qx]
          }
       }
       __syncthreads();
@@ -327,8 +332,8 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
 #pragma unroll
             for (int d = 0; d < D1D; d++)
             {
-               xb[d] = Bx[qx + Q1D*(d + D1D*fz)];
-               xg[d] = Gx[qx + Q1D*(d + D1D*fz)];
+               xb[d] = Bx[qx + QP*(d + D1D*fz)];
+               xg[d] = Gx[qx + QP*(d + D1D*fz)];
             }
             pencil_fwd<D1D,Q1D>(tab.B, xb, bb);
             pencil_fwd<D1D,Q1D>(tab.B, xg, gb);
@@ -346,7 +351,7 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
             const int qx = r % Q1D, lz = r / Q1D;
             double in[L1D], out[Q1D];
 #pragma unroll
-            for (int l = 0; l < L1D; l++) { in[l] = E1[qx + Q1D*(l + L1D*lz)]; }
+            for (int l = 0; l < L1D; l++) { in[l] = E1[qx + QP*(l + L1D*lz)]; }
             pencil_fwd<L1D,Q1D>(tab.BL, in, out);
 #pragma unroll
             for (int q = 0; q < Q1D; q++) { E2[qx + Q1D*(q + Q1D*lz)] = out[q]; }   // [lz][qy][qx]
@@ -413,11 +418,13 @@ template<int D1D, int Q1D>
 struct Force3DCfg
 {
    static constexpr int L1D = D1D - 1, DD = D1D*D1D, QQ = Q1D*Q1D, ND = D1D*DD, NQ = Q1D*QQ, NL = L1D*L1D*L1D;
-   static constexpr int S_W = 9*D1D*QQ;          // W[c][g][dz][qy][qx]; later the element result [c][ND]
-   static constexpr int S_V = 3*DD*Q1D;          // each of VA, VB [c][dz][dy][qx]
-   static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
+   static constexpr int QP = Q1D | 1, DP = D1D | 1, LP = L1D | 1;   // odd row strides (bank-conflict free pencils)
+   static constexpr int S_W = 9*D1D*QQ;          // W[c][g][dz][qy][qx]; later the element result [c][DD rows of DP]
+   static constexpr int S_V = 3*DD*QP;           // each of VA, VB [c][dz][dy][qx]
+   static constexpr int S_ES = L1D*L1D*LP;       // the element's L2 dofs, rows padded
+   static constexpr int S_E1 = L1D*L1D*QP, S_E2 = L1D*QQ;
    // region R1 = W ; region R2 = max(VA|VB, Es|E1|E2|Eq) (the L2 scratch is dead after the z pass)
-   static constexpr int S_L2 = NL + S_E1 + S_E2 + NQ;
+   static constexpr int S_L2 = S_ES + S_E1 + S_E2 + NQ;
    static constexpr int S_R2 = (2*S_V > S_L2) ? 2*S_V : S_L2;
    static constexpr int PER_ELEM = S_W + S_R2;
 };
@@ -433,8 +440,9 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    constexpr int PE = C::PER_ELEM, QQ = C::QQ, DD = C::DD;
    double *W = smem;                             // [e][S_W]
    double *R2 = smem + C::S_W;                   // [e][S_R2], element stride PE for both
-   double *Es = R2, *E1 = Es + C::NL, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2;
+   double *Es = R2, *E1 = Es + C::S_ES, *E2 = E1 + C::S_E1, *Eq = E2 + C::S_E2;
    double *VA = R2, *VB = R2 + C::S_V;
+   constexpr int QP = C::QP, DP = C::DP;
    const int tid = threadIdx.x;
    const int eb = blockIdx.x*NB;
    const int nel = min(NB, NE - eb);
@@ -442,7 +450,7 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    double *Ss = smem + NB*PE;                    // [e][cg][q], PREFETCH only
    if (PREFETCH)
    {
-      static_assert(C::NQ % 2 == 0, "16-byte chunks");
+      static_assert(C::NQ % 2 == 0 && (NB*PE) % 2 == 0, "16-byte chunks");
       constexpr int NCH = 9*C::NQ/2;
       for (int it = tid; it < nel*NCH; it += NT)
       {
@@ -455,7 +463,7 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    for (int it = tid; it < nel*C::NL; it += NT)
    {
       const int e = it / C::NL, i = it - e*C::NL;
-      Es[e*PE + i] = x[(size_t)(eb + e)*C::NL + i];
+      Es[e*PE + i % C::L1D + C::LP*(i / C::L1D)] = x[(size_t)(eb + e)*C::NL + i];
    }
    __syncthreads();
    l2_values<C::L1D,Q1D>(tab.BL, nel, Es, PE, E1, PE, E2, PE, Eq, PE, tid, NT);
@@ -536,7 +544,7 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
 #pragma unroll
       for (int dy = 0; dy < D1D; dy++)
       {
-         const int o = e*PE + qx + Q1D*(dy + D1D*(dz + D1D*c));     // [c][dz][dy][qx]
+         const int o = e*PE + qx + QP*(dy + D1D*(dz + D1D*c));     // [c][dz][dy][qx], rows padded to QP
          VA[o] = a[dy]; VB[o] = b1[dy] + b2[dy];
       }
    }
@@ -548,7 +556,7 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
       const int e = it / (3*DD), r = it - e*(3*DD);       // r = dy + D*(dz + D*c)
       double va[Q1D], vb[Q1D], oa[D1D], ob[D1D];
 #pragma unroll
-      for (int qx = 0; qx < Q1D; qx++) { va[qx] = VA[e*PE + qx + Q1D*r]; vb[qx] = VB[e*PE + qx + Q1D*r]; }
+      for (int qx = 0; qx < Q1D; qx++) { va[qx] = VA[e*PE + qx + QP*r]; vb[qx] = VB[e*PE + qx + QP*r]; }
       pencil_bwd<D1D,Q1D>(tab.G, va, oa);
       pencil_bwd<D1D,Q1D>(tab.B, vb, ob);
 #pragma unroll
@@ -556,7 +564,7 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
       {
          double o = oa[dx] + ob[dx];
          if (fabs(o) < eps2) { o = 0.0; }                 // reference laghos_assembly.cpp:495-512
-         W[e*PE + dx + D1D*r] = o;
+         W[e*PE + dx + DP*r] = o;
       }
    }
    __syncthreads();
@@ -565,7 +573,7 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    {
       const int e = it / (3*C::ND), r = it - e*(3*C::ND);
       const int i = r % C::ND, c = r / C::ND;
-      atomicAdd(y + (size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i), W[e*PE + r]);
+      atomicAdd(y + (size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i), W[e*PE + i % D1D + DP*(i / D1D + DD*c)]);
    }
 }
 
@@ -577,10 +585,11 @@ struct ForceT3DCfg
 {
    static constexpr int L1D = D1D - 1, DD = D1D*D1D, QQ = Q1D*Q1D, ND = D1D*DD, NQ = Q1D*QQ, NL = L1D*L1D*L1D;
    static constexpr int NF = 3;
-   static constexpr int S_ST1 = NF*DD*Q1D, S_ST2 = NF*D1D*QQ;
-   static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
+   static constexpr int QP = Q1D | 1, DP = D1D | 1;      // odd row strides (bank-conflict free pencils)
+   static constexpr int S_ST1 = NF*DD*QP, S_ST2 = NF*D1D*QQ;
+   static constexpr int S_E1 = L1D*L1D*QP, S_E2 = L1D*QQ;
    // region A: Vs -> BB|GB|BG -> t1 ; region B: Bx|Gx -> t2
-   static constexpr int S_A = (3*S_ST2 > NF*ND) ? 3*S_ST2 : NF*ND;
+   static constexpr int S_A = (3*S_ST2 > NF*DD*DP) ? 3*S_ST2 : NF*DD*DP;
    static constexpr int S_B = (2*S_ST1 > S_E2) ? 2*S_ST1 : S_E2;
    static constexpr int PER_ELEM = S_A + S_B;
    static constexpr int S_PF = 9*NQ;             // stressJinvT slab of one element (prefetch variant)
@@ -607,7 +616,7 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
    {
       // the element's 9 stressJinvT planes stream into shared memory while the gather and
       // the x/y pencils run (NQ is even and the planes are 16-byte aligned)
-      static_assert(C::NQ % 2 == 0, "16-byte chunks");
+      static_assert(C::NQ % 2 == 0 && (NB*PE) % 2 == 0, "16-byte chunks");
       constexpr int NCH = 9*C::NQ/2;
       for (int it = tid; it < nel*NCH; it += NT)
       {
@@ -621,7 +630,7 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
    {
       const int e = it / (C::NF*C::ND), r = it - e*(C::NF*C::ND);
       const int i = r % C::ND, c = r / C::ND;
-      Vs[e*PE + r] = v[(size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i)];
+      Vs[e*PE + i % D1D + C::DP*(i / D1D + C::DD*c)] = v[(size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i)];
    }
    __syncthreads();
    grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, nel, Vs, PE, Bx, Gx, PE, BB, GB, BG, PE, tid, NT);
@@ -684,8 +693,10 @@ template<int D1D, int Q1D>
 struct MassL2Cfg
 {
    static constexpr int L1D = D1D - 1, QQ = Q1D*Q1D, NQ = Q1D*QQ, NL = L1D*L1D*L1D;
-   static constexpr int S_E1 = L1D*L1D*Q1D, S_E2 = L1D*QQ;
-   static constexpr int PER_ELEM = NL + S_E1 + S_E2;
+   static constexpr int QP = Q1D | 1, LP = L1D | 1;      // odd row strides (bank-conflict free pencils)
+   static constexpr int S_ES = L1D*L1D*LP;
+   static constexpr int S_E1 = L1D*L1D*QP, S_E2 = L1D*QQ;
+   static constexpr int PER_ELEM = S_ES + S_E1 + S_E2;
 };
 
 template<int D1D, int Q1D, int NB, int NT>
@@ -695,15 +706,15 @@ massl2_3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE,
 {
    using C = MassL2Cfg<D1D,Q1D>;
    extern __shared__ double smem[];
-   constexpr int PE = C::PER_ELEM, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D;
-   double *Es = smem, *t1 = Es + C::NL, *t2 = t1 + C::S_E1;
+   constexpr int PE = C::PER_ELEM, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D, QP = C::QP, LP = C::LP;
+   double *Es = smem, *t1 = Es + C::S_ES, *t2 = t1 + C::S_E1;
    const int tid = threadIdx.x;
    const int eb = blockIdx.x*NB;
    const int nel = min(NB, NE - eb);
    for (int it = tid; it < nel*C::NL; it += NT)
    {
       const int e = it / C::NL, i = it - e*C::NL;
-      Es[e*PE + i] = x[(size_t)(eb + e)*C::NL + i];
+      Es[e*PE + i % L1D + LP*(i / L1D)] = x[(size_t)(eb + e)*C::NL + i];
    }
    __syncthreads();
    for (int it = tid; it < nel*LL; it += NT)              // x pencils
@@ -711,10 +722,10 @@ massl2_3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE,
       const int e = it / LL, r = it - e*LL;
       double in[L1D], out[Q1D];
 #pragma unroll
-      for (int l = 0; l < L1D; l++) { in[l] = Es[e*PE + l + L1D*r]; }
+      for (int l = 0; l < L1D; l++) { in[l] = Es[e*PE + l + LP*r]; }
       pencil_fwd<L1D,Q1D>(tab.BL, in, out);
 #pragma unroll
-      for (int q = 0; q < Q1D; q++) { t1[e*PE + q + Q1D*r] = out[q]; }
+      for (int q = 0; q < Q1D; q++) { t1[e*PE + q + QP*r] = out[q]; }
    }
    __syncthreads();
    for (int it = tid; it < nel*L1D*Q1D; it += NT)         // y pencils
@@ -723,7 +734,7 @@ massl2_3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE,
       const int qx = r % Q1D, lz = r / Q1D;
       double in[L1D], out[Q1D];
 #pragma unroll
-      for (int l = 0; l < L1D; l++) { in[l] = t1[e*PE + qx + Q1D*(l + L1D*lz)]; }
+      for (int l = 0; l < L1D; l++) { in[l] = t1[e*PE + qx + QP*(l + L1D*lz)]; }
       pencil_fwd<L1D,Q1D>(tab.BL, in, out);
 #pragma unroll
       for (int q = 0; q < Q1D; q++) { t2[e*PE + qx + Q1D*(q + Q1D*lz)] = out[q]; }

@@ -5,6 +5,7 @@
 #include "device/mass3d_brick.cuh"
 #include "device/mass3d_brick3.cuh"
 #include "device/staged3d.cuh"
+#include "device/mass3d_pencil.cuh"
 
 namespace lagb {
 
@@ -40,8 +41,7 @@ struct TunedLaunch3D
       { int rc = set_smem(c, kern, Cfg::SMEM_BYTES); if (rc) { return rc; } }
       const int grid = (c.NE + NB - 1)/NB;
       if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
-      kern<<<grid, Cfg::T, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_massD, x, y, c.d_part);
-      LAGB_LAUNCH_CHECK();
+      LAGB_LAUNCH_K(c, kern, grid, Cfg::T, Cfg::SMEM_BYTES, tab(c), c.NE, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y, c.d_part);
       if (WITH_DEN) { c.dt_nblocks = grid; }
       return LAGB_OK;
    }
@@ -70,8 +70,47 @@ struct TunedLaunch3D
          }
          return mass_launch_v<NC,WITH_DEN,8,8,true,true>(c, x, y);
       }
+      if constexpr (D1D >= 5)
+      {
+         // pencil kernel (device/mass3d_pencil.cuh) against the slice kernel, measured on box01_hex -rs 4 (us):
+         //   Q4Q3  1 comp 165 / 284   3 comp 345 / 343        Q5Q4  1 comp 880 / 417   3 comp 1574 / 1142
+         // -> pencils only for the single-component apply at Q4Q3; lagb_tune_set key 0 = 5..7 selects them elsewhere
+         constexpr int NBP = (NC == 1) ? ((D1D == 5) ? 8 : 4) : ((D1D == 5) ? 4 : 2);
+         switch (c.tune[0])
+         {
+            case 5: return pencil_launch<NC,WITH_DEN,NBP,256>(c, x, y);
+            case 6: return pencil_launch<NC,WITH_DEN,(NBP > 1 ? NBP/2 : 1),256>(c, x, y);
+            case 7: return pencil_launch<NC,WITH_DEN,NBP*2,256>(c, x, y);
+         }
+         if constexpr (D1D == 5 && NC == 1) { return pencil_launch<NC,WITH_DEN,NBP,256>(c, x, y); }
+      }
+      if constexpr (D1D == 3 && NC == 3)   // Q2Q1 tuning variants (lagb_tune_set key 0)
+      {
+         switch (c.tune[0])
+         {
+            case 1: return mass_launch_v<NC,WITH_DEN,16,2,true,true>(c, x, y);
+            case 2: return mass_launch_v<NC,WITH_DEN,64,1,true,true>(c, x, y);
+            case 3: return mass_launch_v<NC,WITH_DEN,32,2,true,true>(c, x, y);
+            case 4: return mass_launch_v<NC,WITH_DEN,16,4,true,true>(c, x, y);
+            case 5: return mass_launch_v<NC,WITH_DEN,8,8,true,true>(c, x, y);
+         }
+      }
       // direct gather / scatter for the low orders; staged through shared memory where registers are tight
       return mass_launch_v<NC,WITH_DEN,(NC == 1) ? NB1 : NB3,(NC == 1) ? MINB1 : MINB3,(D1D <= 3),(D1D <= 3)>(c, x, y);
+   }
+   template<int NC, bool WITH_DEN, int NB, int NT>
+   static int pencil_launch(Ctx &c, const double *x, double *y)
+   {
+      using Cfg = tuned::MassPencilCfg<D1D,Q1D,NC>;
+      auto kern = tuned::mass3d_pencil<D1D,Q1D,NB,NC,NT,WITH_DEN>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*NC*Cfg::PER_EC;
+      if (bytes > 227*1024) { set_error("mass3d_pencil: this launch variant does not fit shared memory at this order"); return LAGB_ERR_INVALID; }
+      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
+      const int grid = (c.NE + NB - 1)/NB;
+      if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d_pencil: partial buffer too small"); return LAGB_ERR_STATE; }
+      LAGB_LAUNCH_K(c, kern, grid, NT, bytes, tab(c), c.NE, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y, c.d_part);
+      if (WITH_DEN) { c.dt_nblocks = grid; }
+      return LAGB_OK;
    }
    // ---- brick schedule (device/mass3d_brick.cuh): one launch per colour, programmatic dependent launch ----
    template<int NC, bool WITH_DEN, bool FUSE, int NB, int MINB>
@@ -264,16 +303,16 @@ struct TunedLaunch3D
       if (nc == 1) { return with_den ? mass_launch<1,true>(c, x, y) : mass_launch<1,false>(c, x, y); }
       set_error("mass3d: nc must be 1 or 3"); return LAGB_ERR_INVALID;
    }
-   template<int MINB>
+   template<int MINB, int NT = NTQ>
    static int qupdate_launch(Ctx &c, const double *S, const QPointParams &prm)
    {
-      static_assert(NTQ % 32 == 0 && NTF % 32 == 0, "CTA sizes must be whole warps");
+      static_assert(NT % 32 == 0 && NTF % 32 == 0, "CTA sizes must be whole warps");
       using Cfg = tuned::QUpd3DCfg<D1D,Q1D>;
-      auto kern = tuned::qupdate3d<D1D,Q1D,NTQ,MINB>;
+      auto kern = tuned::qupdate3d<D1D,Q1D,NT,MINB>;
       { int rc = set_smem(c, kern, Cfg::SMEM_BYTES); if (rc) { return rc; } }
       const int grid = c.NE;
-      kern<<<grid, NTQ, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
-                                                    c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_dt);
+      kern<<<grid, NT, Cfg::SMEM_BYTES, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, S, c.d_rho0DetJ0w, c.d_Jac0inv,
+                                                   c.d_gamma, c.d_qweights, c.d_inv_qweights, prm, c.d_sJit, c.d_dt);
       LAGB_LAUNCH_CHECK();
       c.dt_nblocks = grid;
       return LAGB_OK;
@@ -291,8 +330,19 @@ struct TunedLaunch3D
          }
          return qupdate_launch<4>(c, S, prm);   // 4 CTAs/SM (72 registers, L1-resident spill) beat 2 CTAs at 128: 8.1 vs 9.9 ms
       }
-      if (Q1D >= 10 || c.tune[2] == 1) { return qupdate_launch<1>(c, S, prm); }   // Q1D = 10: one CTA per SM by shared memory
-      return qupdate_launch<2>(c, S, prm);
+      else                        // Q1D >= 8: threads per element (points per thread) and resident CTAs
+      {
+         switch (c.tune[2])
+         {
+            case 1: return qupdate_launch<1,256>(c, S, prm);
+            case 2: return qupdate_launch<1,512>(c, S, prm);
+            case 3: return qupdate_launch<2,512>(c, S, prm);
+            case 4: return qupdate_launch<2,384>(c, S, prm);
+            case 5: return qupdate_launch<3,256>(c, S, prm);
+         }
+         if (Q1D >= 10) { return qupdate_launch<1,512>(c, S, prm); }   // 8.5 vs 11.2 ms with 256 threads (box01_hex -rs 4 -ok 5)
+         return qupdate_launch<2>(c, S, prm);
+      }
    }
    template<int NB, int NT, bool PF = false>
    static int force_launch(Ctx &c, const double *e, double *v)
@@ -300,6 +350,7 @@ struct TunedLaunch3D
       using Cfg = tuned::Force3DCfg<D1D,Q1D>;
       auto kern = tuned::force3d<D1D,Q1D,NB,NT,PF>;
       constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + (PF ? 9*Cfg::NQ : 0));
+      if (bytes > 227*1024) { set_error("force3d: this launch variant does not fit shared memory at this order"); return LAGB_ERR_INVALID; }
       { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, e, v);
       LAGB_LAUNCH_CHECK();
@@ -311,6 +362,7 @@ struct TunedLaunch3D
       using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
       auto kern = tuned::forcet3d<D1D,Q1D,NB,NT,PF>;
       constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + (PF ? Cfg::S_PF : 0));
+      if (bytes > 227*1024) { set_error("forcet3d: this launch variant does not fit shared memory at this order"); return LAGB_ERR_INVALID; }
       { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
       kern<<<(c.NE + NB - 1)/NB, NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
       LAGB_LAUNCH_CHECK();
@@ -328,6 +380,30 @@ struct TunedLaunch3D
             case 4: return force_launch<1,192>(c, e, v);
          }
       }
+      if constexpr (D1D >= 5)   // tuning variants of the high orders (lagb_tune_set key 1)
+      {
+         switch (c.tune[1])
+         {
+            case 1: return force_launch<NBF,NTF>(c, e, v);
+            case 2: return force_launch<1,256>(c, e, v);
+            case 3: return force_launch<4,256>(c, e, v);
+            case 4: return force_launch<1,128,true>(c, e, v);
+            case 5: return force_launch<1,256,true>(c, e, v);
+         }
+         // one element, 128 threads: 702 vs 1666 us (Q4Q3), 1900 vs 2569 us (Q5Q4) on box01_hex -rs 4 (profiles/r2_order_sweep.md)
+         return force_launch<1,128>(c, e, v);
+      }
+      if constexpr (D1D == 3)
+      {
+         switch (c.tune[1])
+         {
+            case 1: return force_launch<4,128>(c, e, v);
+            case 2: return force_launch<16,256>(c, e, v);
+            case 3: return force_launch<8,128>(c, e, v);
+            case 4: return force_launch<4,256>(c, e, v);
+            case 5: return force_launch<2,64>(c, e, v);
+         }
+      }
       return force_launch<NBF,NTF>(c, e, v);
    }
    static int force_mult_t(Ctx &c, const double *v, double *e)
@@ -342,6 +418,31 @@ struct TunedLaunch3D
             case 4: return forcet_launch<1,64>(c, v, e);
          }
          return forcet_launch<1,96,true>(c, v, e);   // cp.async prefetch of the stressJinvT slab
+      }
+      if constexpr (D1D >= 5)
+      {
+         switch (c.tune[1])
+         {
+            case 1: return forcet_launch<1,128>(c, v, e);
+            case 2: return forcet_launch<1,256>(c, v, e);
+            case 3: return forcet_launch<4,256>(c, v, e);
+            case 4: return forcet_launch<NBF,NTF>(c, v, e);
+            case 5: return forcet_launch<1,(D1D == 5) ? 256 : 128,true>(c, v, e);
+         }
+         // one element per CTA with the bulk-prefetched stressJinvT slab: 1082 vs 3322 us (Q4Q3, 128 threads),
+         // 2932 vs 4119 us (Q5Q4, 256 threads)
+         return forcet_launch<1,(D1D == 5) ? 128 : 256,true>(c, v, e);
+      }
+      if constexpr (D1D == 3)
+      {
+         switch (c.tune[1])
+         {
+            case 1: return forcet_launch<4,128>(c, v, e);
+            case 2: return forcet_launch<16,256>(c, v, e);
+            case 3: return forcet_launch<8,128>(c, v, e);
+            case 4: return forcet_launch<4,256>(c, v, e);
+            case 5: return forcet_launch<2,64>(c, v, e);
+         }
       }
       return forcet_launch<NBF,NTF>(c, v, e);
    }

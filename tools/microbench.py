@@ -53,9 +53,14 @@ def main():
     yv = c.empty(nv)
     c.qupdate(dS)
 
+    class Unavailable(Exception):
+        pass
+
     def timeit(fn, reps=args.reps):
         for _ in range(2):
-            fn()
+            rc = fn()
+            if isinstance(rc, int) and rc != 0:
+                raise Unavailable(c.lib.lagb_last_error().decode())
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         ev[0].record()
@@ -68,7 +73,15 @@ def main():
 
     rows = []
 
-    def report(name, us, gbytes, out=None):
+    def report(name, fn_or_us, gbytes, out=None):
+        if callable(fn_or_us):
+            try:
+                us = timeit(fn_or_us)
+            except Unavailable as ex:
+                print(f"{name:38s} unavailable: {ex}", flush=True)
+                return
+        else:
+            us = fn_or_us
         bw = gbytes / (us * 1e-6)
         rows.append((name, us, gbytes, bw, bw / peak))
         chk = "" if out is None else f"  checksum {float(out.double().abs().sum()):.15e}"
@@ -78,15 +91,15 @@ def main():
     only = set(args.only.split(",")) if args.only else {"q", "force", "mass", "l2", "pcg"}
     for var in ([int(s) for s in args.q_variants.split(",")] if "q" in only else []):
         c.tune(2, var)
-        report(f"qupdate (fused) variant {var}", timeit(lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
+        report(f"qupdate (fused) variant {var}", (lambda: c.lib.lagb_qupdate_async(c.h, c._p(dS), 0.5)),
                8e-9 * (2 * dim * nd + nl + NE * NQ * (1 + 2 * dim * dim)), c.qdata(0))
     c.tune(2, 0)
     ye = c.empty(nl)
     for var in ([int(s) for s in args.force_variants.split(",")] if "force" in only else []):
         c.tune(1, var)
-        report(f"force_mult variant {var}", timeit(lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
+        report(f"force_mult variant {var}", (lambda: c.lib.lagb_force_mult(c.h, c._p(e), c._p(yv))),
                8e-9 * (dim * dim * NE * NQ + nl + dim * nd), yv)
-        report(f"force_mult_transpose variant {var}", timeit(lambda: c.lib.lagb_force_mult_transpose(c.h, c._p(v), c._p(ye))),
+        report(f"force_mult_transpose variant {var}", (lambda: c.lib.lagb_force_mult_transpose(c.h, c._p(v), c._p(ye))),
                8e-9 * (dim * dim * NE * NQ + nl + dim * nd), ye)
     c.tune(1, 0)
     y1 = c.empty(nd)
@@ -111,12 +124,12 @@ def main():
     c.tune(6, 1)   # legacy atomic-scatter kernels
     for var in ([int(s) for s in args.mass1_variants.split(",")] if "mass" in only else []):
         c.tune(3, var)
-        report(f"vmass_mult (1 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
+        report(f"vmass_mult (1 comp) variant {var}", (lambda: c.lib.lagb_vmass_mult(c.h, -1, c._p(x1), c._p(y1))),
                8e-9 * (NE * NQ + 2 * nd), y1)
     c.tune(3, 0)
     for var in ([int(s) for s in args.mass_variants.split(",")] if "mass" in only else []):
         c.tune(0, var)
-        report(f"vmass_mult_all (3 comp) variant {var}", timeit(lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
+        report(f"vmass_mult_all (3 comp) variant {var}", (lambda: c.lib.lagb_vmass_mult_all(c.h, c._p(v), c._p(yv))),
                8e-9 * (NE * NQ + 2 * dim * nd), yv)
     c.tune(0, 0)
     c.tune(6, 0)
