@@ -192,22 +192,36 @@ __global__ void halo_combine(int nu, int nc, int64_t cstride, const int *__restr
 // (P^t then P in the reference's RAP operator, laghos_assembly.cpp:95 / SURVEY 8e):
 // per phase, pack -> grouped ncclSend/ncclRecv -> add.  After all phases every
 // sharing rank holds the same fully summed value.
+// peer-memory exchange in two halves so that work can be enqueued in between: pack straight into the neighbours'
+// receive areas and raise the flags / wait for the neighbours' flags and combine
+static bool halo_p2p(const Ctx &c) { return c.nranks > 1 && !c.nbrs.empty() && c.halo_single && c.p2p_on && c.tune[11] == 0; }
+int halo_begin_p2p(Ctx &c, const double *v, int nc)
+{
+   const unsigned long long seq = ++c.p2p_halo_seq;
+   const int nnbr = (int)c.nbrs.size();
+   const int g = std::max(1, std::min(296, (c.halo_total + 255)/256));
+   LAGB_LAUNCH_K(c, p2p::halo_pack_p2p, g, 256, 0, c.p2p_dev, seq, c.halo_total, nc, (int64_t)c.ndofs, (const int*)c.d_pack_idx,
+                 (const unsigned char*)c.d_pack_nb, (const int*)c.d_nbr_off, (const int*)c.d_nbr_n, (const int*)c.d_nbr_roff,
+                 (const int*)c.d_nbr_rank, nnbr, v, c.d_pack_done);
+   return LAGB_OK;
+}
+int halo_end_p2p(Ctx &c, double *v, int nc)
+{
+   const unsigned long long seq = c.p2p_halo_seq;
+   const int nnbr = (int)c.nbrs.size();
+   LAGB_LAUNCH_K(c, p2p::halo_combine_p2p, std::max(1, std::min(296, (c.halo_nu + 255)/256)), 256, 0, c.p2p_dev, seq, c.halo_nu, nc,
+                 (int64_t)c.ndofs, (const int*)c.d_u_dof, (const int*)c.d_u_ptr, (const int*)c.d_u_src, (const unsigned char*)c.d_pack_nb,
+                 (const int*)c.d_nbr_off, (const int*)c.d_nbr_n, (const int*)c.d_nbr_rank, nnbr, v);
+   return LAGB_OK;
+}
+
 int halo_sum(Ctx &c, double *v, int nc)
 {
    if (c.nranks <= 1 || c.nbrs.empty()) { return LAGB_OK; }
-   if (c.halo_single && c.p2p_on && c.tune[11] == 0)
+   if (halo_p2p(c))
    {
-      // peer-memory exchange: pack straight into the neighbours' receive areas, flags instead of send/recv
-      const unsigned long long seq = ++c.p2p_halo_seq;
-      const int nnbr = (int)c.nbrs.size();
-      const int g = std::max(1, std::min(296, (c.halo_total + 255)/256));
-      LAGB_LAUNCH_K(c, p2p::halo_pack_p2p, g, 256, 0, c.p2p_dev, seq, c.halo_total, nc, (int64_t)c.ndofs, (const int*)c.d_pack_idx,
-                    (const unsigned char*)c.d_pack_nb, (const int*)c.d_nbr_off, (const int*)c.d_nbr_n, (const int*)c.d_nbr_roff,
-                    (const int*)c.d_nbr_rank, nnbr, (const double*)v, c.d_pack_done);
-      LAGB_LAUNCH_K(c, p2p::halo_combine_p2p, std::max(1, std::min(296, (c.halo_nu + 255)/256)), 256, 0, c.p2p_dev, seq, c.halo_nu, nc,
-                    (int64_t)c.ndofs, (const int*)c.d_u_dof, (const int*)c.d_u_ptr, (const int*)c.d_u_src, (const unsigned char*)c.d_pack_nb,
-                    (const int*)c.d_nbr_off, (const int*)c.d_nbr_n, (const int*)c.d_nbr_rank, nnbr, v);
-      return LAGB_OK;
+      int rc = halo_begin_p2p(c, v, nc); if (rc) { return rc; }
+      return halo_end_p2p(c, v, nc);
    }
    if (c.halo_single)
    {
@@ -446,6 +460,27 @@ static int p2p_setup(Ctx &c, int nnbr, const int32_t *nbr_rank)
    }
    { int rc = dev_alloc(&c.d_pack_done, 1); if (rc) { return rc; } LAGB_CUDA(cudaMemset(c.d_pack_done, 0, sizeof(unsigned int))); }
    { int rc = dev_upload(&c.d_p2p_dev, &c.p2p_dev, 1); if (rc) { return rc; } }
+   if (c.halo_single)
+   {
+      // elements that touch a shared dof first (ascending), then the others (ascending)
+      std::vector<unsigned char> shared((size_t)c.ndofs, 0);
+      for (auto &nb : c.nbrs) { (void)nb; }
+      {
+         std::vector<int> idx((size_t)c.halo_total);
+         LAGB_CUDA(cudaMemcpy(idx.data(), c.d_pack_idx, sizeof(int)*idx.size(), cudaMemcpyDeviceToHost));
+         for (int i : idx) { shared[i] = 1; }
+      }
+      std::vector<int> bnd, inner;
+      for (int e = 0; e < c.NE; e++)
+      {
+         bool b = false;
+         for (int i = 0; i < c.ND && !b; i++) { b = shared[c.h_map[(size_t)e*c.ND + i]] != 0; }
+         (b ? bnd : inner).push_back(e);
+      }
+      c.n_bnd_elems = (int)bnd.size();
+      bnd.insert(bnd.end(), inner.begin(), inner.end());
+      int rc = dev_upload(&c.d_elist, bnd.data(), bnd.size()); if (rc) { return rc; }
+   }
    c.p2p_on = true;
    return LAGB_OK;
 }
@@ -471,6 +506,41 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    // H1 apply through the atomic-free brick kernels (plain stores): no zero fill of z anywhere
    const bool bapply = !l2 && c.variant == 0 && ks.mass_brick != nullptr && c.tune[6] >= 2 && (NC == 1 || NC == 3);
    const bool zero_z = !l2 && !bapply;   // only the atomic scatter accumulates into z
+   // Zero fill of A d off the critical path: two result buffers alternate, and the one an iteration has just
+   // consumed (update_r) is cleared on an auxiliary stream while the direction update and the NEXT operator apply
+   // run (the mass kernel is LSU / fp64 bound at 36 % of the HBM bandwidth, so the 172 MB memset is free there).
+   // Invariant: a buffer not in use is zero, or its memset is pending behind c.ev_zclr[i].
+   const bool zalt = zero_z && c.tune[13] == 0 && c.aux_stream != nullptr && c.tune[8] == 0;
+   double *zb[2] = {c.d_z, c.d_d2};
+   int zi = 0;
+   auto z_acquire = [&](int i) -> int
+   {
+      if (c.z_pending[i]) { LAGB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_zclr[i], 0)); c.z_pending[i] = false; }
+      return LAGB_OK;
+   };
+   auto z_release = [&](int i) -> int     // after the last reader of zb[i] has been enqueued
+   {
+      LAGB_CUDA(cudaEventRecord(c.ev_zuse, c.stream));
+      LAGB_CUDA(cudaStreamWaitEvent(c.aux_stream, c.ev_zuse, 0));
+      LAGB_CUDA(cudaMemsetAsync(zb[i], 0, sizeof(double)*NC*n, c.aux_stream));
+      LAGB_CUDA(cudaEventRecord(c.ev_zclr[i], c.aux_stream));
+      c.z_pending[i] = true;
+      return LAGB_OK;
+   };
+   if (zalt)
+   {
+      if (!c.z_clean)
+      {
+         // another path (brick kernels, experiments) used the buffers as scratch: restore the invariant once
+         LAGB_CUDA(cudaStreamSynchronize(c.aux_stream));
+         c.z_pending[0] = c.z_pending[1] = false;
+         LAGB_CUDA(cudaMemsetAsync(zb[0], 0, sizeof(double)*(size_t)c.ndofs*c.dim, c.stream));
+         LAGB_CUDA(cudaMemsetAsync(zb[1], 0, sizeof(double)*(size_t)c.ndofs*c.dim, c.stream));
+         c.z_clean = true;
+      }
+      int rz = z_acquire(0); if (rz) { return rz; }
+      z = zb[0];
+   }
 
    // apply: z (+)= A v ; returns number of partial blocks if the kernel produced d^t A d partials
    size_t den_src_off = 0;     // where the operator's d^t A d partials start inside d_part
@@ -480,6 +550,18 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       if (l2) { return ks.mass_l2(c, v, z); }
       if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
       int rc;
+      // multi rank, peer memory: the elements that touch shared dofs first, their partial sums travel to the
+      // neighbours while the interior elements are applied (the exchange latency and the rank skew hide there)
+      const bool split = !bapply && halo_p2p(c) && ks.mass_h1_part != nullptr && c.d_elist != nullptr && NC == 3 && c.tune[14] == 0;
+      if (split)
+      {
+         rc = ks.mass_h1_part(c, NC, v, z, want_den, 0); if (rc) { return rc; }
+         rc = halo_begin_p2p(c, z, NC); if (rc) { return rc; }
+         rc = ks.mass_h1_part(c, NC, v, z, want_den, 1); if (rc) { return rc; }
+         if (c.profile_mass) { int rt = timer_end(c, 4); if (rt) { return rt; } c.mass_launches++; }
+         if (want_den) { den_blocks = c.dt_nblocks; den_src_off = 0; }
+         return halo_end_p2p(c, z, NC);
+      }
       if (bapply) { MassBrickIn in; in.x = v; rc = ks.mass_brick(c, NC, in, z, want_den); }
       else { rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass); }
       if (rc) { return rc; }
@@ -509,7 +591,7 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    const double *src = nullptr;
    if (iterative_mode)
    {
-      if (zero_z) { LAGB_CUDA(cudaMemsetAsync(z, 0, sizeof(double)*NC*n, c.stream)); }
+      if (zero_z && !zalt) { LAGB_CUDA(cudaMemsetAsync(z, 0, sizeof(double)*NC*n, c.stream)); }
       rc = apply(x, false, den_blocks); if (rc) { return rc; }
    }
    else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
@@ -534,6 +616,7 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    while (!finished && it < max_iter)
    {
       it++;
+      if (zalt) { rc = z_acquire(zi); if (rc) { return rc; } z = zb[zi]; }
       rc = apply(d, true, den_blocks); if (rc) { return rc; }
       if (den_blocks == 0)
       {
@@ -554,10 +637,11 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       {
          // same arithmetic, one vector pass less: x is updated where d is read anyway
          LAGB_LAUNCH_K(c, pcg::update_r<NC>, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, r, (const double*)z, P, own, c.d_part);
+         if (zalt) { rc = z_release(zi); if (rc) { return rc; } zi ^= 1; }
          rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
          LAGB_LAUNCH_K(c, pcg::finish_beta<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, it, max_iter, pd, pseq, c.d_fin, c.d_grp_ctr);
          auto kz = pcg::update_dx<NC,true>; auto kn = pcg::update_dx<NC,false>;
-         LAGB_LAUNCH_K(c, zero_z ? kz : kn, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, x, d, (const double*)r, P, z);
+         LAGB_LAUNCH_K(c, (zero_z && !zalt) ? kz : kn, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, x, d, (const double*)r, P, z);
       }
       if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
    }
@@ -581,6 +665,8 @@ static int pcg_run_brick(Ctx &c, int comp0, const double *b, double *x, double r
    const int64_t n = c.ndofs, cs = n;
    double *r = c.d_r, *z = c.d_z;
    double *dcur = c.d_d, *dnxt = c.d_d2;
+   c.z_clean = false;     // both buffers are scratch here (pcg_run_nc restores its zero invariant on its next solve)
+   if (c.aux_stream) { LAGB_CUDA(cudaStreamSynchronize(c.aux_stream)); c.z_pending[0] = c.z_pending[1] = false; }
    pcg::Prec P; P.dinv = c.d_dinv; P.ess = c.d_essmask; P.comp0 = comp0;
    const unsigned char *own = c.d_own;
    const int g = vec_grid(n);
@@ -767,6 +853,12 @@ int lagb_ctx_create(lagb_ctx **out, const lagb_ctx_desc *d, void *stream)
    auto finish = [&]() -> int
    {
       LAGB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+      LAGB_CUDA(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
+      LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_zuse, cudaEventDisableTiming));
+      LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_zclr[0], cudaEventDisableTiming));
+      LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_zclr[1], cudaEventDisableTiming));
+      LAGB_CUDA(cudaMemset(c.d_z, 0, sizeof(double)*(size_t)c.ndofs*c.dim));
+      LAGB_CUDA(cudaMemset(c.d_d2, 0, sizeof(double)*(size_t)c.ndofs*c.dim));
       LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_compute, cudaEventDisableTiming));
       LAGB_CUDA(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
       LAGB_CUDA(cudaMallocHost((void**)&c.h_state, sizeof(pcg::State)));
@@ -811,6 +903,8 @@ void lagb_ctx_destroy(lagb_ctx *h)
    void *hp[] = {c.d_pack_idx, c.d_pack_nb, c.d_nbr_off, c.d_nbr_n, c.d_u_dof, c.d_u_ptr, c.d_u_src, c.d_send_all, c.d_recv_all};
    for (void *p : hp) { if (p) { cudaFree(p); } }
    if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); }
+   if (c.aux_stream) { cudaStreamSynchronize(c.aux_stream); cudaStreamDestroy(c.aux_stream); }
+   { cudaEvent_t ev[] = {c.ev_zuse, c.ev_zclr[0], c.ev_zclr[1]}; for (cudaEvent_t e : ev) { if (e) { cudaEventDestroy(e); } } }
    if (c.ev_compute) { cudaEventDestroy(c.ev_compute); }
    if (c.ev_copy) { cudaEventDestroy(c.ev_copy); }
    if (c.h_state) { cudaFreeHost(c.h_state); }
@@ -818,7 +912,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (int w = 0; w < Timer::NT; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
    for (auto e : c.timer.pool) { cudaEventDestroy(e); }
    for (void *p : c.p2p_opened) { cudaIpcCloseMemHandle(p); }
-   { void *pp[] = {c.p2p_base, c.d_nbr_roff, c.d_nbr_rank, c.d_pack_done, c.d_p2p_dev}; for (void *p : pp) { if (p) { cudaFree(p); } } }
+   { void *pp[] = {c.p2p_base, c.d_nbr_roff, c.d_nbr_rank, c.d_pack_done, c.d_p2p_dev, c.d_elist}; for (void *p : pp) { if (p) { cudaFree(p); } } }
    if (c.nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c.nccl_comm); }
    delete h;
 }
@@ -828,6 +922,7 @@ int lagb_ctx_sync(lagb_ctx *h)
    LAGB_ENTER(h);
    LAGB_CUDA(cudaStreamSynchronize(h->c.stream));
    if (h->c.copy_stream) { LAGB_CUDA(cudaStreamSynchronize(h->c.copy_stream)); }
+   if (h->c.aux_stream) { LAGB_CUDA(cudaStreamSynchronize(h->c.aux_stream)); }
    return LAGB_OK;
 }
 
@@ -1109,12 +1204,13 @@ int lagb_kinetic_energy(lagb_ctx *h, const double *d_v, double *h_out)
    if (!c.setup_done) { set_error("kinetic_energy: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    const int64_t n = c.ndofs*c.dim;
-   LAGB_CUDA(cudaMemsetAsync(c.d_z, 0, sizeof(double)*n, c.stream));
+   // scratch: the PCG residual vector (d_z / d_d2 stay zero between solves, see pcg_run_nc)
+   LAGB_CUDA(cudaMemsetAsync(c.d_r, 0, sizeof(double)*n, c.stream));
    // rank-local element contributions only (no shared-dof sum): v^t (M_loc v) summed over ranks
    // counts every element once
-   int rc = ks.mass_h1(c, c.dim, d_v, c.d_z, false); if (rc) { return rc; }
+   int rc = ks.mass_h1(c, c.dim, d_v, c.d_r, false); if (rc) { return rc; }
    double s = 0.0;
-   rc = global_dot(c, d_v, c.d_z, n, &s); if (rc) { return rc; }
+   rc = global_dot(c, d_v, c.d_r, n, &s); if (rc) { return rc; }
    *h_out = 0.5*s;
    return LAGB_OK;
 }

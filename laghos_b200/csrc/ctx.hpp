@@ -64,6 +64,8 @@ struct DevPlan
 struct KernelSet
 {
    int (*mass_h1)(Ctx&, int nc, const double *x, double *y, bool with_den) = nullptr; // y += M x (nc comps, byNODES stride)
+   // the same over part 0 (elements touching shared dofs) / part 1 (the rest) of c.d_elist; nullptr where not instantiated
+   int (*mass_h1_part)(Ctx&, int nc, const double *x, double *y, bool with_den, int part) = nullptr;
    // y = M x without atomics (coloured brick schedule); nullptr where not instantiated
    int (*mass_brick)(Ctx&, int nc, const MassBrickIn &in, double *y, bool with_den) = nullptr;
    int (*mass_diag)(Ctx&, double *diag) = nullptr;
@@ -97,6 +99,8 @@ struct Ctx
    cudaStream_t stream = nullptr;
    cudaStream_t copy_stream = nullptr;               // background state transfers (lagb_memcpy_*_bg)
    cudaEvent_t ev_compute = nullptr, ev_copy = nullptr;
+   cudaStream_t aux_stream = nullptr;                // clears the PCG's idle result buffer behind the iteration
+   cudaEvent_t ev_zuse = nullptr, ev_zclr[2] = {nullptr, nullptr}; bool z_pending[2] = {false, false}; bool z_clean = true;
    KernelSet ks, ks_generic;
    std::vector<unsigned char> tab_blob;   // DevTables<D1D,Q1D> bytes
    // device arrays
@@ -134,7 +138,9 @@ struct Ctx
    // [7] brick shape (0 cube-like, 1 x-long, 2 x-pencil), [8] 1 = first PCG vector kernels (update_xr/update_d),
    // [9] 1 = plain (not fused) PCG on the multi-launch brick kernels, [10] 1 = energy solve by the reference's CG
    // instead of the element inverses, [11] 1 = NCCL send/recv + all-reduce instead of the peer-memory exchanges,
-   // [12] 1 = plain launches (no programmatic dependent launch) in the PCG iteration
+   // [12] 1 = plain launches (no programmatic dependent launch) in the PCG iteration,
+   // [13] 1 = zero fill of A d inside the direction kernel (one result buffer) instead of the alternating buffers,
+   // [14] 1 = multi rank: one mass launch, then the exchange (no boundary-first split)
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing
@@ -159,6 +165,7 @@ struct Ctx
    std::vector<void*> p2p_opened;                   // peers' mappings (cudaIpcCloseMemHandle on destroy)
    unsigned long long p2p_scal_seq = 0, p2p_halo_seq = 0;
    int *d_nbr_roff = nullptr, *d_nbr_rank = nullptr; unsigned int *d_pack_done = nullptr;
+   int *d_elist = nullptr; int n_bnd_elems = 0;     // [NE] elements touching shared dofs first, then the others (ascending)
 };
 
 // helpers implemented in capi.cu
