@@ -281,6 +281,15 @@ def main():
         tp = os.path.join(ROOT, "profiles", "mass3d_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        # the batched mass apply is fp64-bound (7.4 flop/byte at Q3Q2 against a machine balance of 5.2): report it
+        # against the measured DFMA peak as well (profiles/r2_fp64_pipe_probe.txt, tools/probes/fp64_pipe_probe.cu)
+        D1, Q1 = args.ok + 1, 2 * args.ok
+        fma_per_ec = 2 * (D1 ** 3 * Q1 + D1 ** 2 * Q1 ** 2 + D1 * Q1 ** 3)
+        flops = float(NE_loc) * ncomp * (2 * fma_per_ec + Q1 ** 3)
+        fp64_peak = 33.8
+        fp64 = {"achieved": flops / avg_s / 1e12 if avg_s > 0 else 0.0, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (flops / avg_s / 1e12 / fp64_peak) if avg_s > 0 else 0.0, "flops_per_launch": flops,
+                "peak_source": "measured DFMA rate (profiles/r2_fp64_pipe_probe.txt)"}
         T_major = r["fom"][4]
         metric = METRIC if (args.problem, args.ok) == (1, 3) else \
             f"Mdof x steps / s (major kernels total rate), 3D {PROBLEM_NAMES.get(args.problem, args.problem)} Q{args.ok}/Q{args.ok - 1} -pa"
@@ -301,7 +310,8 @@ def main():
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": 1e6 * avg_s, "launches": nl,
-                         "share_of_major_time": r["mass_kernel_seconds"] / T_major if T_major > 0 else None},
+                         "share_of_major_time": r["mass_kernel_seconds"] / T_major if T_major > 0 else None,
+                         "fp64": fp64},
             "e2e": e2e, "gpu_launches": int(r["kernel_launches"]), "clocks": clocks,
             "e_norm": r["e_norm"],
             # |e| after the same number of steps by the CPU oracle (tests/golden/bench_enorm.json); north_star bar 1e-9

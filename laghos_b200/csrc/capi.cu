@@ -550,9 +550,11 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       if (l2) { return ks.mass_l2(c, v, z); }
       if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
       int rc;
-      // multi rank, peer memory: the elements that touch shared dofs first, their partial sums travel to the
-      // neighbours while the interior elements are applied (the exchange latency and the rank skew hide there)
-      const bool split = !bapply && halo_p2p(c) && ks.mass_h1_part != nullptr && c.d_elist != nullptr && NC == 3 && c.tune[14] == 0;
+      // multi rank, peer memory, opt-in (lagb_tune_set key 14 = 1): the elements that touch shared dofs first, their
+      // partial sums travel to the neighbours while the interior elements are applied.  Measured SLOWER at 2 ranks
+      // (97.7 vs 93.8 ms per step): the element-list indirection puts a dependent load in front of every CTA's D
+      // prefetch and the face elements gather without coalescing; the exchange it hides costs less than that.
+      const bool split = !bapply && halo_p2p(c) && ks.mass_h1_part != nullptr && c.d_elist != nullptr && NC == 3 && c.tune[14] == 1;
       if (split)
       {
          rc = ks.mass_h1_part(c, NC, v, z, want_den, 0); if (rc) { return rc; }
