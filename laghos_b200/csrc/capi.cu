@@ -23,6 +23,21 @@ int vec_grid(int64_t n)
    return (int)std::max<int64_t>(1, std::min<int64_t>(b, 148*16));
 }
 
+// One-wave grid of a grid-stride vector kernel: resident CTAs per SM (occupancy API, cached per context) x SMs.
+// vec_grid() assumes 16 CTAs per SM; the load-first PCG kernels hold 80-114 registers (2-3 CTAs per SM), so that grid
+// ran in 4-8 waves of CTAs with 3 loop iterations each and a block reduction per CTA (update_r: 60 % of the HBM peak).
+template<typename K>
+static int wave_grid(Ctx &c, K kern, int64_t n)
+{
+   int &occ = c.occ_cache[(const void*)kern];
+   if (occ == 0)
+   {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pcg::RB, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 2; }
+   }
+   const int64_t b = (n + pcg::RB - 1)/pcg::RB;
+   return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)c.num_sms*occ));
+}
+
 // ---- timers: CUDA events on the context stream, resolved lazily ----
 static cudaEvent_t timer_event(Ctx &c)
 {
@@ -502,6 +517,10 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
    const unsigned char *own = l2 ? nullptr : c.d_own;
    const int g = vec_grid(n);
    if (g*NC > c.part_cap) { set_error("pcg: partial buffer too small"); return LAGB_ERR_STATE; }
+   // one-wave grids of the two per-iteration vector kernels (lagb_tune_set key 15 = 1: the fixed 148*16 grid)
+   const bool wave = c.tune[15] == 0;
+   const int g_r = wave ? wave_grid(c, pcg::update_r<NC>, n) : g;
+   const int g_dx = wave ? std::min(wave_grid(c, pcg::update_dx<NC,true>, n), wave_grid(c, pcg::update_dx<NC,false>, n)) : g;
    KernelSet &ks = (c.variant == 1) ? c.ks_generic : c.ks;
    // H1 apply through the atomic-free brick kernels (plain stores): no zero fill of z anywhere
    const bool bapply = !l2 && c.variant == 0 && ks.mass_brick != nullptr && c.tune[6] >= 2 && (NC == 1 || NC == 3);
@@ -638,12 +657,12 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       else
       {
          // same arithmetic, one vector pass less: x is updated where d is read anyway
-         LAGB_LAUNCH_K(c, pcg::update_r<NC>, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, r, (const double*)z, P, own, c.d_part);
+         LAGB_LAUNCH_K(c, pcg::update_r<NC>, g_r, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, r, (const double*)z, P, own, c.d_part);
          if (zalt) { rc = z_release(zi); if (rc) { return rc; } zi ^= 1; }
-         rc = reduced(g, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
+         rc = reduced(g_r, c.d_tmp + 4, src, nsrc); if (rc) { return rc; }
          LAGB_LAUNCH_K(c, pcg::finish_beta<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, it, max_iter, pd, pseq, c.d_fin, c.d_grp_ctr);
          auto kz = pcg::update_dx<NC,true>; auto kn = pcg::update_dx<NC,false>;
-         LAGB_LAUNCH_K(c, (zero_z && !zalt) ? kz : kn, g, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, x, d, (const double*)r, P, z);
+         LAGB_LAUNCH_K(c, (zero_z && !zalt) ? kz : kn, g_dx, pcg::RB, 0, n, cs, (const pcg::State*)c.d_state, x, d, (const double*)r, P, z);
       }
       if (it >= next_check) { rc = poll(); if (rc) { return rc; } }
    }

@@ -140,6 +140,7 @@ struct Ctx
    // instead of the element inverses, [11] 1 = NCCL send/recv + all-reduce instead of the peer-memory exchanges,
    // [12] 1 = plain launches (no programmatic dependent launch) in the PCG iteration,
    // [13] 1 = zero fill of A d inside the direction kernel (one result buffer) instead of the alternating buffers,
+   // [15] 1 = fixed 148*16 grid for the PCG vector kernels instead of one wave (occupancy x SMs),
    // [14] 1 = multi rank: boundary elements first, exchange under the interior launch (measured slower: opt-in)
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
