@@ -295,21 +295,19 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
    {
       constexpr int DD = C::DD, QQ = C::QQ, L1D = C::L1D, LL = L1D*L1D, QP = C::QP, DP = C::DP, LP = C::LP;
       const double *Es = A + C::NF*DD*DP;
-      // stage alpha: x pencils, one item per (pencil, table): 2*96 + 9 items of 24 FMAs keep 201 of the 224 threads
-      // busy (one item per pencil with both tables: 105 threads, twice the latency under the barrier)
-      constexpr int nGa = 2*C::NF*DD, nLa = LL;
+      // stage alpha: x pencils
+      constexpr int nGa = C::NF*DD, nLa = LL;
       for (int it = tid; it < nGa + nLa; it += NT)
       {
          if (it < nGa)
          {
-            const int which = it / (C::NF*DD), pen = it - which*(C::NF*DD);   // warps are uniform in `which`
-            double in[D1D], o[Q1D];
+            double in[D1D], bo[Q1D], go[Q1D];
 #pragma unroll
-            for (int d = 0; d < D1D; d++) { in[d] = A[d + DP*pen]; }
-            if (which == 0) { pencil_fwd<D1D,Q1D>(tab.B, in, o); } else { pencil_fwd<D1D,Q1D>(tab.G, in, o); }
-            double *dst = (which == 0) ? Bx : Gx;
+            for (int d = 0; d < D1D; d++) { in[d] = A[d + DP*it]; }
+            pencil_fwd<D1D,Q1D>(tab.B, in, bo);
+            pencil_fwd<D1D,Q1D>(tab.G, in, go);
 #pragma unroll
-            for (int q = 0; q < Q1D; q++) { dst[q + QP*pen] = o[q]; }
+            for (int q = 0; q < Q1D; q++) { Bx[q + QP*it] = bo[q]; Gx[q + QP*it] = go[q]; }
          }
          else
          {
@@ -323,22 +321,29 @@ qupdate3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const in
          }
       }
       __syncthreads();
-      // stage beta: y pencils (BB | GB | BG overwrite the dofs, which are dead now), one item per (pencil, output array)
-      constexpr int nGb = 3*C::NF*D1D*Q1D, nLb = L1D*Q1D;
+      // stage beta: y pencils (BB | GB | BG overwrite the dofs, which are dead now)
+      constexpr int nGb = C::NF*D1D*Q1D, nLb = L1D*Q1D;
       for (int it = tid; it < nGb + nLb; it += NT)
       {
          if (it < nGb)
          {
-            const int which = it / (C::NF*D1D*Q1D), pen = it - which*(C::NF*D1D*Q1D);
-            const int qx = pen % Q1D, fz = pen / Q1D;   // fz = dz + D1D*f
-            const double *srcp = (which == 1) ? Gx : Bx;               // BB = B Bx, GB = B Gx, BG = G Bx
-            double xin[D1D], o[Q1D];
+            const int qx = it % Q1D, fz = it / Q1D;   // fz = dz + D1D*f
+            double xb[D1D], xg[D1D], bb[Q1D], gb[Q1D], bg[Q1D];
 #pragma unroll
-            for (int d = 0; d < D1D; d++) { xin[d] = srcp[qx + QP*(d + D1D*fz)]; }
-            if (which == 2) { pencil_fwd<D1D,Q1D>(tab.G, xin, o); } else { pencil_fwd<D1D,Q1D>(tab.B, xin, o); }
-            double *dst = (which == 0) ? BB : (which == 1) ? GB : BG;
+            for (int d = 0; d < D1D; d++)
+            {
+               xb[d] = Bx[qx + QP*(d + D1D*fz)];
+               xg[d] = Gx[qx + QP*(d + D1D*fz)];
+            }
+            pencil_fwd<D1D,Q1D>(tab.B, xb, bb);
+            pencil_fwd<D1D,Q1D>(tab.B, xg, gb);
+            pencil_fwd<D1D,Q1D>(tab.G, xb, bg);
 #pragma unroll
-            for (int q = 0; q < Q1D; q++) { dst[qx + Q1D*q + QQ*fz] = o[q]; }   // [f][dz][qy][qx]
+            for (int q = 0; q < Q1D; q++)
+            {
+               const int o = qx + Q1D*q + QQ*fz;      // [f][dz][qy][qx]
+               BB[o] = bb[q]; GB[o] = gb[q]; BG[o] = bg[q];
+            }
          }
          else
          {
