@@ -448,6 +448,17 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    const int nel = min(NB, NE - eb);
    const size_t NEQ = (size_t)NE*C::NQ;
    double *Ss = smem + NB*PE;                    // [e][cg][q], PREFETCH only
+   // restriction indices of this thread's scatter items: requested first, used last (ncu: 10 % of the kernel's stall
+   // samples sat on this load when it was issued inside the scatter loop at the end of the CTA)
+   constexpr int NSC = (NB*3*C::ND + NT - 1)/NT;
+   int sidx[NSC];
+#pragma unroll
+   for (int k = 0; k < NSC; k++)
+   {
+      const int it = tid + k*NT;
+      const int e = it / (3*C::ND), r = it - e*(3*C::ND);
+      sidx[k] = (it < nel*3*C::ND) ? __ldg(map + (size_t)(eb + e)*C::ND + r % C::ND) : 0;
+   }
    if (PREFETCH)
    {
       static_assert(C::NQ % 2 == 0 && (NB*PE) % 2 == 0, "16-byte chunks");
@@ -569,11 +580,16 @@ force3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int6
    }
    __syncthreads();
    // scatter-add, lanes along the element-local dof index
-   for (int it = tid; it < nel*3*C::ND; it += NT)
+#pragma unroll
+   for (int k = 0; k < NSC; k++)
    {
-      const int e = it / (3*C::ND), r = it - e*(3*C::ND);
-      const int i = r % C::ND, c = r / C::ND;
-      atomicAdd(y + (size_t)c*ndofs + __ldg(map + (size_t)(eb + e)*C::ND + i), W[e*PE + i % D1D + DP*(i / D1D + DD*c)]);
+      const int it = tid + k*NT;
+      if (it < nel*3*C::ND)
+      {
+         const int e = it / (3*C::ND), r = it - e*(3*C::ND);
+         const int i = r % C::ND, c = r / C::ND;
+         atomicAdd(y + (size_t)c*ndofs + sidx[k], W[e*PE + i % D1D + DP*(i / D1D + DD*c)]);
+      }
    }
 }
 
@@ -684,6 +700,132 @@ forcet3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int
    }
    __syncthreads();
    l2_values_t_yx<C::L1D,Q1D>(tab.BL, nel, t2, PE, t1, PE, eout + (size_t)eb*C::NL, tid, NT);
+}
+
+// ---------------------------------------------------------------------------
+// Force transpose, persistent: a CTA walks over element batches bi = blockIdx.x, + gridDim.x, ... and keeps the
+// gather of the NEXT batch in flight (values in registers, the indices of the batch after that as well) while it
+// works on the current one.  ncu of the one-batch-per-CTA kernel: 27 % of all stall samples sit on the dependent
+// index -> value loads of the gather at the start of every 9-us CTA, another 18 % on the barriers behind it.
+// The stressJinvT slab of the batch is bulk-prefetched (cp.async) as before.  Measured 1358 vs 1452 us (cfg 2).
+// Tried on top and dropped: z pencils split over the three components with a 3-lane shuffle reduction (108 busy
+// threads instead of 36 in that stage): 1607 us with 128 threads, 2039 us with 96.
+// ---------------------------------------------------------------------------
+template<int D1D, int Q1D, int NB, int NT>
+__global__ void __launch_bounds__(NT)
+forcet3d_persist(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t ndofs,
+                 const int *__restrict__ map, const double *__restrict__ sJit,
+                 const double *__restrict__ v, double *__restrict__ eout)
+{
+   using C = ForceT3DCfg<D1D,Q1D>;
+   extern __shared__ double smem[];
+   constexpr int PE = C::PER_ELEM, QQ = C::QQ;
+   double *RA = smem, *RB = smem + C::S_A;
+   double *Vs = RA, *BB = RA, *GB = RA + C::S_ST2, *BG = RA + 2*C::S_ST2, *t1 = RA;
+   double *Bx = RB, *Gx = RB + C::S_ST1, *t2 = RB;
+   double *Ss = smem + NB*PE;                    // [e][cg][q]
+   static_assert(C::NQ % 2 == 0 && (NB*PE) % 2 == 0, "16-byte chunks");
+   const int tid = threadIdx.x;
+   const size_t NEQ = (size_t)NE*C::NQ;
+   const int nbatch = (NE + NB - 1)/NB;
+   constexpr int PER = NB*C::NF*C::ND;            // gathered values per batch
+   constexpr int NIT = (PER + NT - 1)/NT;
+   int idx_n[NIT];                                // restriction indices of the batch after the next
+   double xr[NIT];                                // gathered values of the next batch
+   auto load_idx = [&](int bi)
+   {
+      const int nd = min(NB, NE - bi*NB)*C::NF*C::ND;
+#pragma unroll
+      for (int k = 0; k < NIT; k++)
+      {
+         const int it = tid + k*NT;
+         const int e = it / (C::NF*C::ND), r = it - e*(C::NF*C::ND);
+         idx_n[k] = (bi < nbatch && it < nd) ? __ldg(map + (size_t)(bi*NB + e)*C::ND + r % C::ND) : 0;
+      }
+   };
+   auto load_val = [&](int bi)                    // uses idx_n (loaded one batch earlier)
+   {
+      const int nd = min(NB, NE - bi*NB)*C::NF*C::ND;
+#pragma unroll
+      for (int k = 0; k < NIT; k++)
+      {
+         const int it = tid + k*NT;
+         const int r = it % (C::NF*C::ND);
+         xr[k] = (bi < nbatch && it < nd) ? v[(size_t)(r / C::ND)*ndofs + idx_n[k]] : 0.0;
+      }
+   };
+   int bi = blockIdx.x;
+   load_idx(bi);
+   load_val(bi);
+   load_idx(bi + gridDim.x);
+   for (; bi < nbatch; bi += gridDim.x)
+   {
+      const int eb = bi*NB;
+      const int nel = min(NB, NE - eb);
+      {
+         constexpr int NCH = 9*C::NQ/2;
+         for (int it = tid; it < nel*NCH; it += NT)
+         {
+            const int e = it / NCH, r = it - e*NCH;
+            const int cg = r / (C::NQ/2), h = r - cg*(C::NQ/2);
+            cp_async16(Ss + (size_t)e*C::S_PF + cg*C::NQ + 2*h, sJit + (size_t)(eb + e)*C::NQ + NEQ*cg + 2*h);
+         }
+         asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+#pragma unroll
+      for (int k = 0; k < NIT; k++)
+      {
+         const int it = tid + k*NT;
+         if (it < nel*C::NF*C::ND)
+         {
+            const int e = it / (C::NF*C::ND), r = it - e*(C::NF*C::ND);
+            const int i = r % C::ND, c = r / C::ND;
+            Vs[e*PE + i % D1D + C::DP*(i / D1D + C::DD*c)] = xr[k];
+         }
+      }
+      __syncthreads();
+      // next batch: values through the indices that arrived during the previous batch, then the indices after that
+      load_val(bi + gridDim.x);
+      load_idx(bi + 2*gridDim.x);
+      grad_xy<D1D,Q1D,C::NF>(tab.B, tab.G, nel, Vs, PE, Bx, Gx, PE, BB, GB, BG, PE, tid, NT);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      for (int it = tid; it < nel*QQ; it += NT)
+      {
+         const int e = it / QQ, col = it - e*QQ;
+         double acc[Q1D];
+#pragma unroll
+         for (int qz = 0; qz < Q1D; qz++) { acc[qz] = 0.0; }
+#pragma unroll
+         for (int c = 0; c < 3; c++)
+         {
+            double bb[D1D], gb[D1D], bg[D1D], g0[Q1D], g1[Q1D], g2[Q1D];
+#pragma unroll
+            for (int dz = 0; dz < D1D; dz++)
+            {
+               const int o = e*PE + col + QQ*(dz + D1D*c);
+               bb[dz] = BB[o]; gb[dz] = GB[o]; bg[dz] = BG[o];
+            }
+            pencil_fwd<D1D,Q1D>(tab.B, gb, g0);
+            pencil_fwd<D1D,Q1D>(tab.B, bg, g1);
+            pencil_fwd<D1D,Q1D>(tab.G, bb, g2);
+#pragma unroll
+            for (int qz = 0; qz < Q1D; qz++)
+            {
+               // same association as the reference (:889-899): per component, sum over g, then add
+               const double *sq = Ss + (size_t)e*C::S_PF + col + QQ*qz;
+               acc[qz] += g0[qz]*sq[C::NQ*(0 + 3*c)] + g1[qz]*sq[C::NQ*(1 + 3*c)] + g2[qz]*sq[C::NQ*(2 + 3*c)];
+            }
+         }
+         double o[C::L1D];
+         pencil_bwd<C::L1D,Q1D>(tab.BL, acc, o);
+#pragma unroll
+         for (int lz = 0; lz < C::L1D; lz++) { t2[e*PE + col + QQ*lz] = o[lz]; }   // Bx|Gx are dead
+      }
+      __syncthreads();
+      l2_values_t_yx<C::L1D,Q1D>(tab.BL, nel, t2, PE, t1, PE, eout + (size_t)eb*C::NL, tid, NT);
+      __syncthreads();     // RA / RB / Ss are rewritten by the next batch
+   }
 }
 
 // ---------------------------------------------------------------------------

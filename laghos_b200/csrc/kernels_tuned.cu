@@ -398,6 +398,25 @@ struct TunedLaunch3D
       LAGB_LAUNCH_CHECK();
       return LAGB_OK;
    }
+   template<int NB, int NT>
+   static int forcet_persist_launch(Ctx &c, const double *v, double *e)
+   {
+      using Cfg = tuned::ForceT3DCfg<D1D,Q1D>;
+      auto kern = tuned::forcet3d_persist<D1D,Q1D,NB,NT>;
+      constexpr size_t bytes = sizeof(double)*(size_t)NB*(Cfg::PER_ELEM + Cfg::S_PF);
+      if (bytes > 227*1024) { set_error("forcet3d: this launch variant does not fit shared memory at this order"); return LAGB_ERR_INVALID; }
+      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
+      int &occ = c.occ_cache[(const void*)kern];
+      if (occ == 0)
+      {
+         LAGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, bytes));
+         if (occ < 1) { set_error("forcet3d_persist does not fit an SM"); return LAGB_ERR_STATE; }
+      }
+      const int nbatch = (c.NE + NB - 1)/NB;
+      kern<<<std::min(nbatch, c.num_sms*occ), NT, bytes, c.stream>>>(tab(c), c.NE, c.ndofs, c.d_map, c.d_sJit, v, e);
+      LAGB_LAUNCH_CHECK();
+      return LAGB_OK;
+   }
    static int force_mult(Ctx &c, const double *e, double *v)
    {
       if constexpr (D1D == 4)   // tuning variants (lagb_tune_set key 1)
@@ -446,8 +465,10 @@ struct TunedLaunch3D
             case 2: return forcet_launch<4,256>(c, v, e);
             case 3: return forcet_launch<1,128,true>(c, v, e);
             case 4: return forcet_launch<1,64>(c, v, e);
+            case 5: return forcet_launch<1,96,true>(c, v, e);   // one element per CTA, cp.async prefetch of the stressJinvT slab
+            case 6: return forcet_persist_launch<1,128>(c, v, e);
          }
-         return forcet_launch<1,96,true>(c, v, e);   // cp.async prefetch of the stressJinvT slab
+         return forcet_persist_launch<1,96>(c, v, e);   // persistent CTAs, next element's gather in flight: 1358 vs 1452 us
       }
       if constexpr (D1D >= 5)
       {
