@@ -432,7 +432,7 @@ update_r(int64_t n, int64_t cstride, const State *__restrict__ st,
          const unsigned char *__restrict__ own, double *__restrict__ part)
 {
    pdl_launch(); pdl_wait();
-   constexpr int UNR = 4;
+   constexpr int UNR = 2;   // 2 iterations in flight: 80 registers, 3 CTAs/SM; 4 (114 registers, 2 CTAs/SM) measured 2.4 % slower on T_cgH1
    __shared__ double sh[32];
    double acc[NC], alpha[NC];
 #pragma unroll
@@ -489,7 +489,7 @@ update_dx(int64_t n, int64_t cstride, const State *__restrict__ st,
           const Prec P, double *__restrict__ z)
 {
    pdl_launch(); pdl_wait();
-   constexpr int UNR = 2;
+   constexpr int UNR = 2;   // 1 iteration in flight measured 1 % slower
    double alpha[NC], beta[NC]; bool skip[NC];
 #pragma unroll
    for (int c = 0; c < NC; c++) { alpha[c] = st->alpha[c]; beta[c] = st->beta[c]; skip[c] = st->done[c] != 0; }
