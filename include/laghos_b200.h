@@ -179,6 +179,11 @@ int lagb_pcg_vmass(lagb_ctx *ctx, int comp, const double *d_b, double *d_x,
  * read once per iteration for all components.  h_iters[c] per component. */
 int lagb_pcg_vmass_all(lagb_ctx *ctx, const double *d_rhs, double *d_dv,
                        double rel_tol, int max_iter, int *h_iters);
+/* The same with a ZERO initial guess (MFEM CGSolver with iterative_mode = false: x = 0, r = b; the reference's
+ * SolveVelocity starts every solve from dv = 0, laghos_solver.cpp:363-398 with dS_dt = 0): d_dv is output only, and
+ * the operator application to the initial guess is skipped.  Same iterates as lagb_pcg_vmass_all on a zeroed d_dv. */
+int lagb_pcg_vmass_all_x0(lagb_ctx *ctx, const double *d_rhs, double *d_dv,
+                          double rel_tol, int max_iter, int *h_iters);
 /* CG_EMass.Mult(e_rhs, de) (laghos_solver.cpp:481): unpreconditioned CG,
  * iterative_mode = false. */
 int lagb_cg_emass(lagb_ctx *ctx, const double *d_b, double *d_x,

@@ -72,7 +72,7 @@ lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_memcpy_h2d_bg lagb_memcpy_d2h_bg lagb
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
 lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set lagb_internal_energy lagb_kinetic_energy
-lagb_host_batch_plan_check lagb_compute_density""".split()
+lagb_host_batch_plan_check lagb_compute_density lagb_pcg_vmass_all_x0""".split()
 
 
 def load_library():
@@ -128,6 +128,7 @@ def load_library():
     lib.lagb_dt_est_read.argtypes = [vp, c_double_p]
     lib.lagb_pcg_vmass.argtypes = [vp, i32, vp, vp, dbl, i32, c_int_p]
     lib.lagb_pcg_vmass_all.argtypes = [vp, vp, vp, dbl, i32, c_int_p]
+    lib.lagb_pcg_vmass_all_x0.argtypes = [vp, vp, vp, dbl, i32, c_int_p]
     lib.lagb_cg_emass.argtypes = [vp, vp, vp, dbl, i32, c_int_p]
     lib.lagb_taylor_source.argtypes = [vp, vp, vp]
     lib.lagb_compute_density.argtypes = [vp, vp, vp]

@@ -237,6 +237,13 @@ class Context:
         _check(self.lib, self.lib.lagb_pcg_vmass_all(self.h, self._p(rhs), self._p(x), rel_tol, max_iter, it))
         return x, [int(it[c]) for c in range(self.P.dim)]
 
+    def pcg_vmass_all_x0(self, rhs, rel_tol=1e-8, max_iter=300):
+        """The batched solve from a zero initial guess (the reference's SolveVelocity): x is output only."""
+        x = self.empty(self.P.h1_vsize)
+        it = (C.c_int32 * 3)()
+        _check(self.lib, self.lib.lagb_pcg_vmass_all_x0(self.h, self._p(rhs), self._p(x), rel_tol, max_iter, it))
+        return x, [int(it[c]) for c in range(self.P.dim)]
+
     def cg_emass(self, b, rel_tol=1e-8, max_iter=300):
         x = self.empty(self.P.ndofs_l2)
         it = C.c_int32()

@@ -616,7 +616,9 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       rc = apply(x, false, den_blocks); if (rc) { return rc; }
    }
    else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
-   LAGB_LAUNCH_K(c, pcg::init_residual<NC>, g, pcg::RB, 0, n, cs, b, z, P, own, r, d, c.d_part, iterative_mode ? 1 : 0);
+   // bit 0: r = b - A x ; bit 1: clear z (not needed when the alternating buffers are clean and no A x was formed)
+   LAGB_LAUNCH_K(c, pcg::init_residual<NC>, g, pcg::RB, 0, n, cs, b, z, P, own, r, d, c.d_part,
+                 (iterative_mode ? 1 : 0) | ((iterative_mode || !zalt) ? 2 : 0));
    rc = reduced(g, c.d_tmp, src, nsrc); if (rc) { return rc; }
    LAGB_LAUNCH_K(c, pcg::finish_init<NC>, fin_grid(nsrc), pcg::FB, 0, c.d_state, src, nsrc, rel_tol, 0.0, pd, pseq, c.d_fin, c.d_grp_ctr);
 
@@ -719,7 +721,7 @@ static int pcg_run_brick(Ctx &c, int comp0, const double *b, double *x, double r
    const double *src = nullptr;
    if (iterative_mode) { MassBrickIn in; in.x = x; rc = apply(in, false); if (rc) { return rc; } }
    else { LAGB_CUDA(cudaMemsetAsync(x, 0, sizeof(double)*NC*n, c.stream)); }
-   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, P, own, r, dcur, c.d_part, iterative_mode ? 1 : 0);
+   pcg::init_residual<NC><<<g, pcg::RB, 0, c.stream>>>(n, cs, b, z, P, own, r, dcur, c.d_part, (iterative_mode ? 1 : 0) | 2);
    LAGB_LAUNCH_CHECK();
    rc = reduced(g, c.d_tmp, src, nsrc); if (rc) { return rc; }
    pcg::finish_init<NC><<<1, pcg::FB, 0, c.stream>>>(c.d_state, src, nsrc, rel_tol, 0.0, nullptr, 0ull, c.d_fin, c.d_grp_ctr);   // beta = 0: first direction = M^-1 r
@@ -1161,6 +1163,19 @@ int lagb_pcg_vmass_all(lagb_ctx *h, const double *d_rhs, double *d_dv, double re
    int rc = timer_begin(c, 0); if (rc) { return rc; }
    int it[3] = {0, 0, 0};
    rc = pcg_run(c, false, c.dim, 0, d_rhs, d_dv, rel_tol, max_iter, true, it); if (rc) { return rc; }
+   rc = timer_end(c, 0); if (rc) { return rc; }
+   for (int k = 0; k < c.dim; k++) { c.H1iter += it[k]; if (iters) { iters[k] = it[k]; } }
+   return LAGB_OK;
+}
+
+int lagb_pcg_vmass_all_x0(lagb_ctx *h, const double *d_rhs, double *d_dv, double rel_tol, int max_iter, int *iters)
+{
+   LAGB_ENTER(h);
+   Ctx &c = h->c;
+   if (!c.setup_done) { set_error("pcg_vmass_all_x0: call lagb_setup_qdata0 first"); return LAGB_ERR_STATE; }
+   int rc = timer_begin(c, 0); if (rc) { return rc; }
+   int it[3] = {0, 0, 0};
+   rc = pcg_run(c, false, c.dim, 0, d_rhs, d_dv, rel_tol, max_iter, false, it); if (rc) { return rc; }
    rc = timer_end(c, 0); if (rc) { return rc; }
    for (int k = 0; k < c.dim; k++) { c.H1iter += it[k]; if (iters) { iters[k] = it[k]; } }
    return LAGB_OK;

@@ -11,7 +11,11 @@
 // arithmetically identical to zeroing the operator rows and the RHS entries
 // (MassPAOperator::Mult / EliminateRHS, reference laghos_assembly.cpp:112-121).
 //
-// All reductions are two-stage with fixed summation order (deterministic).
+// The inner products are reduced in a fixed order (per CTA, then per finish-kernel chunk, then across ranks in
+// ascending rank order): for given input vectors they are bit-reproducible.  The operator's E -> L scatter is not:
+// it adds with red.global.add.f64, so A d (and from there the iterates) can differ in the last bits from run to run;
+// iteration counts are stable to +-1 and |e| to ~1e-12 (tests/test_gpu_end_to_end.py).  The deterministic scatter
+// exists (coloured brick schedule, lagb_tune_set key 6) but is slower.
 #pragma once
 #include "common.cuh"
 #include "p2p_prims.cuh"
@@ -77,9 +81,10 @@ __global__ void init_residual(int64_t n, int64_t cstride, const double *__restri
       for (int c = 0; c < NC; c++)
       {
          const int64_t k = i + c*cstride;
-         const double rr = iterative_mode ? b[k] - z[k] : b[k];
+         const double rr = (iterative_mode & 1) ? b[k] - z[k] : b[k];
          const double zz = prec_apply(P, i, c, rr);
-         r[k] = rr; d[k] = zz; z[k] = 0.0;
+         r[k] = rr; d[k] = zz;
+         if (iterative_mode & 2) { z[k] = 0.0; }      // bit 1: leave a zeroed result vector behind
          acc[c] += w*zz*rr;
       }
    }

@@ -95,7 +95,7 @@ void LagrangianHydroOperator::SolveVelocity(const Vector &S, Vector &dS_dt) cons
    UpdateQuadratureData(S);
    Vector dv;
    dv.MakeRef(dS_dt, H1Vsize, H1Vsize);
-   dv = 0.0;
+   if (!batched_pcg) { dv = 0.0; }      // the batched solve starts from zero itself (lagb_pcg_vmass_all_x0)
    ForcePA->Mult(one, rhs);
    rhs.Neg();
    if (source_type == 2) { rhs.Add(1.0, accel_b); }
@@ -105,7 +105,8 @@ void LagrangianHydroOperator::SolveVelocity(const Vector &S, Vector &dS_dt) cons
       // all components in one batched device PCG: the quadrature data is streamed
       // once per iteration for the `dim` solves of laghos_solver.cpp:363-398
       int it[3];
-      LAGHOS_CHECK(lagb_pcg_vmass_all(ctx, rhs.Read(), dv.Write(), cg_rel_tol, cg_max_iter, it));
+      // zero initial guess (dS_dt = 0 in the reference): x = 0, r = b, no operator application before the loop
+      LAGHOS_CHECK(lagb_pcg_vmass_all_x0(ctx, rhs.Read(), dv.Write(), cg_rel_tol, cg_max_iter, it));
    }
    else
    {

@@ -154,6 +154,22 @@ def test_pcg_tight_tolerance(pair):
         assert relerr(x.cpu().numpy(), xr) < 1e-11
 
 
+def test_pcg_zero_guess_entry(pair):
+    """lagb_pcg_vmass_all_x0 (x = 0, r = b, no initial operator application) gives the iterates of lagb_pcg_vmass_all
+    started from a zeroed vector: same iteration counts, same solution to round-off."""
+    P, O, ctxs = pair
+    if P.dim != 3:
+        pytest.skip("batched 3-component solve")
+    v = np.random.default_rng(21).uniform(-1, 1, P.h1_vsize)
+    for c in ctxs:
+        xa, ia = c.pcg_vmass_all(c.dev(v))
+        xb, ib = c.pcg_vmass_all_x0(c.dev(v))
+        # two solves stopped at rel. 1e-8 whose scatters sum in a different order: iteration counts within 1,
+        # solutions within the solver tolerance
+        assert all(abs(a - b) <= 1 for a, b in zip(ia, ib))
+        assert relerr(xb.cpu().numpy(), xa.cpu().numpy()) < 1e-7
+
+
 def test_cg_emass(pair):
     P, O, ctxs = pair
     b = np.random.default_rng(13).uniform(-1, 1, P.ndofs_l2)
