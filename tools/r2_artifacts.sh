@@ -2,6 +2,7 @@
 # Round-2 measurement artifacts on one B200 (run under gpurun): outputs under gpurun_out/, copied to profiles/ here.
 export LAGB_HEAD=$(cat .lagb_head 2>/dev/null || echo unknown)
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/a_gpu_tests.log 2>&1; tail -2 gpurun_out/a_gpu_tests.log
 # 1. headline bench lines
 python bench.py > gpurun_out/a_bench_1gpu.json 2> gpurun_out/a_bench_1gpu.err
 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/a_bench_1gpu_20steps.json 2>> gpurun_out/a_bench_1gpu.err
@@ -18,6 +19,7 @@ tools/ncu_capture.sh a_update_dx 'update_dx' --op pcg --reps 1
 tools/ncu_capture.sh a_l2inv_apply 'l2inv_apply' --op cgl2 --reps 2
 tools/ncu_capture.sh a_force3d '^force3d' --op force --reps 2
 tools/ncu_capture.sh a_forcet3d 'forcet3d' --op forcet --reps 2
+tools/ncu_capture.sh a_qupdate3d 'qupdate3d' --op q --reps 2
 # 4. sanitizers at this commit
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/a_sanitize_memcheck.txt 2>&1
 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py --quick > gpurun_out/a_sanitize_racecheck.txt 2>&1
