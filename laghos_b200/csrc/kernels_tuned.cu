@@ -479,10 +479,13 @@ struct TunedLaunch3D
             case 3: return forcet_launch<4,256>(c, v, e);
             case 4: return forcet_launch<NBF,NTF>(c, v, e);
             case 5: return forcet_launch<1,(D1D == 5) ? 256 : 128,true>(c, v, e);
+            case 6: return forcet_launch<1,(D1D == 5) ? 128 : 256,true>(c, v, e);
+            case 7: return forcet_persist_launch<1,(D1D == 5) ? 256 : 128>(c, v, e);
          }
-         // one element per CTA with the bulk-prefetched stressJinvT slab: 1082 vs 3322 us (Q4Q3, 128 threads),
-         // 2932 vs 4119 us (Q5Q4, 256 threads)
-         return forcet_launch<1,(D1D == 5) ? 128 : 256,true>(c, v, e);
+         // persistent CTAs, one element per batch, next element's gather in flight, cp.async stressJinvT slab:
+         // Q4Q3 (128 threads) 777 us (2 elements x 256 threads: 3322, one element per CTA + slab: 1042),
+         // Q5Q4 (256 threads) 2393 us (4119, 2932); key 1 = 4: the round-1 shape, 5 / 7: the other thread count
+         return forcet_persist_launch<1,(D1D == 5) ? 128 : 256>(c, v, e);
       }
       if constexpr (D1D == 3)
       {
@@ -493,7 +496,10 @@ struct TunedLaunch3D
             case 3: return forcet_launch<8,128>(c, v, e);
             case 4: return forcet_launch<4,256>(c, v, e);
             case 5: return forcet_launch<2,64>(c, v, e);
+            case 6: return forcet_persist_launch<8,256>(c, v, e);
+            case 7: return forcet_launch<NBF,NTF>(c, v, e);
          }
+         return forcet_persist_launch<4,128>(c, v, e);   // Q2Q1: 113 us (8 elements x 256 threads per CTA: 145)
       }
       return forcet_launch<NBF,NTF>(c, v, e);
    }
