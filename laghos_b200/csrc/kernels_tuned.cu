@@ -6,6 +6,7 @@
 #include "device/mass3d_brick3.cuh"
 #include "device/staged3d.cuh"
 #include "device/mass3d_pencil.cuh"
+#include "device/mass3d_persist.cuh"
 
 namespace lagb {
 
@@ -75,6 +76,26 @@ struct TunedLaunch3D
       }
       set_error("mass3d: no listed variant for this order / component count"); return LAGB_ERR_INVALID;
    }
+   template<int NC, bool WITH_DEN, int NB, int MINB>
+   static int mass_persist_launch(Ctx &c, const double *x, double *y)
+   {
+      using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
+      auto kern = tuned::mass3d_persist<D1D,Q1D,NB,NC,WITH_DEN,MINB>;
+      const size_t bytes = Cfg::SMEM_BYTES + (size_t)NB*D1D*Cfg::IDXS*sizeof(int);    // second index buffer
+      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
+      int &occ = c.occ_cache[(const void*)kern];
+      if (occ == 0)
+      {
+         LAGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::T, bytes));
+         if (occ < 1) { set_error("mass3d_persist does not fit an SM"); return LAGB_ERR_STATE; }
+      }
+      const int nbatch = (c.NE + NB - 1)/NB;
+      const int grid = std::min(nbatch, c.num_sms*occ);
+      if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
+      LAGB_LAUNCH_K(c, kern, grid, Cfg::T, bytes, tab(c), c.NE, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y, c.d_part);
+      if (WITH_DEN) { c.dt_nblocks = grid; }
+      return LAGB_OK;
+   }
    template<int NC, bool WITH_DEN>
    static int mass_launch(Ctx &c, const double *x, double *y)
    {
@@ -86,6 +107,8 @@ struct TunedLaunch3D
             case 2: return mass_launch_v<NC,WITH_DEN,16,3,true,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
+            case 5: return mass_persist_launch<NC,WITH_DEN,8,6>(c, x, y);
+            case 6: return mass_persist_launch<NC,WITH_DEN,8,5>(c, x, y);
          }
          return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants*.txt): 351 us
       }
