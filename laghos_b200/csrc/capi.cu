@@ -475,27 +475,6 @@ static int p2p_setup(Ctx &c, int nnbr, const int32_t *nbr_rank)
    }
    { int rc = dev_alloc(&c.d_pack_done, 1); if (rc) { return rc; } LAGB_CUDA(cudaMemset(c.d_pack_done, 0, sizeof(unsigned int))); }
    { int rc = dev_upload(&c.d_p2p_dev, &c.p2p_dev, 1); if (rc) { return rc; } }
-   if (c.halo_single)
-   {
-      // elements that touch a shared dof first (ascending), then the others (ascending)
-      std::vector<unsigned char> shared((size_t)c.ndofs, 0);
-      for (auto &nb : c.nbrs) { (void)nb; }
-      {
-         std::vector<int> idx((size_t)c.halo_total);
-         LAGB_CUDA(cudaMemcpy(idx.data(), c.d_pack_idx, sizeof(int)*idx.size(), cudaMemcpyDeviceToHost));
-         for (int i : idx) { shared[i] = 1; }
-      }
-      std::vector<int> bnd, inner;
-      for (int e = 0; e < c.NE; e++)
-      {
-         bool b = false;
-         for (int i = 0; i < c.ND && !b; i++) { b = shared[c.h_map[(size_t)e*c.ND + i]] != 0; }
-         (b ? bnd : inner).push_back(e);
-      }
-      c.n_bnd_elems = (int)bnd.size();
-      bnd.insert(bnd.end(), inner.begin(), inner.end());
-      int rc = dev_upload(&c.d_elist, bnd.data(), bnd.size()); if (rc) { return rc; }
-   }
    c.p2p_on = true;
    return LAGB_OK;
 }
@@ -569,20 +548,6 @@ static int pcg_run_nc(Ctx &c, bool l2, int comp0, const double *b, double *x, do
       if (l2) { return ks.mass_l2(c, v, z); }
       if (c.profile_mass) { int rt = timer_begin(c, 4); if (rt) { return rt; } }
       int rc;
-      // multi rank, peer memory, opt-in (lagb_tune_set key 14 = 1): the elements that touch shared dofs first, their
-      // partial sums travel to the neighbours while the interior elements are applied.  Measured SLOWER at 2 ranks
-      // (97.7 vs 93.8 ms per step): the element-list indirection puts a dependent load in front of every CTA's D
-      // prefetch and the face elements gather without coalescing; the exchange it hides costs less than that.
-      const bool split = !bapply && halo_p2p(c) && ks.mass_h1_part != nullptr && c.d_elist != nullptr && NC == 3 && c.tune[14] == 1;
-      if (split)
-      {
-         rc = ks.mass_h1_part(c, NC, v, z, want_den, 0); if (rc) { return rc; }
-         rc = halo_begin_p2p(c, z, NC); if (rc) { return rc; }
-         rc = ks.mass_h1_part(c, NC, v, z, want_den, 1); if (rc) { return rc; }
-         if (c.profile_mass) { int rt = timer_end(c, 4); if (rt) { return rt; } c.mass_launches++; }
-         if (want_den) { den_blocks = c.dt_nblocks; den_src_off = 0; }
-         return halo_end_p2p(c, z, NC);
-      }
       if (bapply) { MassBrickIn in; in.x = v; rc = ks.mass_brick(c, NC, in, z, want_den); }
       else { rc = ks.mass_h1(c, NC, v, z, want_den && ks.tuned_mass); }
       if (rc) { return rc; }
@@ -935,7 +900,7 @@ void lagb_ctx_destroy(lagb_ctx *h)
    for (int w = 0; w < Timer::NT; w++) { for (auto &p : c.timer.pending[w]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
    for (auto e : c.timer.pool) { cudaEventDestroy(e); }
    for (void *p : c.p2p_opened) { cudaIpcCloseMemHandle(p); }
-   { void *pp[] = {c.p2p_base, c.d_nbr_roff, c.d_nbr_rank, c.d_pack_done, c.d_p2p_dev, c.d_elist}; for (void *p : pp) { if (p) { cudaFree(p); } } }
+   { void *pp[] = {c.p2p_base, c.d_nbr_roff, c.d_nbr_rank, c.d_pack_done, c.d_p2p_dev}; for (void *p : pp) { if (p) { cudaFree(p); } } }
    if (c.nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c.nccl_comm); }
    delete h;
 }

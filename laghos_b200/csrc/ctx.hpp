@@ -64,8 +64,6 @@ struct DevPlan
 struct KernelSet
 {
    int (*mass_h1)(Ctx&, int nc, const double *x, double *y, bool with_den) = nullptr; // y += M x (nc comps, byNODES stride)
-   // the same over part 0 (elements touching shared dofs) / part 1 (the rest) of c.d_elist; nullptr where not instantiated
-   int (*mass_h1_part)(Ctx&, int nc, const double *x, double *y, bool with_den, int part) = nullptr;
    // y = M x without atomics (coloured brick schedule); nullptr where not instantiated
    int (*mass_brick)(Ctx&, int nc, const MassBrickIn &in, double *y, bool with_den) = nullptr;
    int (*mass_diag)(Ctx&, double *diag) = nullptr;
@@ -140,8 +138,7 @@ struct Ctx
    // instead of the element inverses, [11] 1 = NCCL send/recv + all-reduce instead of the peer-memory exchanges,
    // [12] 1 = plain launches (no programmatic dependent launch) in the PCG iteration,
    // [13] 1 = zero fill of A d inside the direction kernel (one result buffer) instead of the alternating buffers,
-   // [15] 1 = fixed 148*16 grid for the PCG vector kernels instead of one wave (occupancy x SMs),
-   // [14] 1 = multi rank: boundary elements first, exchange under the interior launch (measured slower: opt-in)
+   // [15] 1 = fixed 148*16 grid for the PCG vector kernels instead of one wave (occupancy x SMs)
    int tune[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
    int predicted_iters = 0;
    // timing
@@ -166,7 +163,6 @@ struct Ctx
    std::vector<void*> p2p_opened;                   // peers' mappings (cudaIpcCloseMemHandle on destroy)
    unsigned long long p2p_scal_seq = 0, p2p_halo_seq = 0;
    int *d_nbr_roff = nullptr, *d_nbr_rank = nullptr; unsigned int *d_pack_done = nullptr;
-   int *d_elist = nullptr; int n_bnd_elems = 0;     // [NE] elements touching shared dofs first, then the others (ascending)
 };
 
 // helpers implemented in capi.cu

@@ -45,14 +45,11 @@ struct Mass3DCfg
    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES*sizeof(double) + (size_t)NB*D1D*IDXS*sizeof(int);
 };
 
-// LISTED: the launch covers the `NE` elements elist[0..NE) instead of 0..NE (multi-rank: the elements that touch
-// shared dofs are applied first so that the shared-dof exchange overlaps the interior launch).
-template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_SCATTER, bool DIRECT_GATHER = false, bool LISTED = false>
+template<int D1D, int Q1D, int NB, int NC, bool WITH_DEN, int MINB, bool DIRECT_SCATTER, bool DIRECT_GATHER = false>
 __global__ void __launch_bounds__(((NC*NB*D1D + 31)/32)*32, MINB)
 mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64_t cstride,
        const int *__restrict__ map, const double *__restrict__ Dq,
-       const double *__restrict__ x, double *__restrict__ y, double *__restrict__ den_part,
-       const int *__restrict__ elist)
+       const double *__restrict__ x, double *__restrict__ y, double *__restrict__ den_part)
 {
    using C = Mass3DCfg<D1D,Q1D,NB,NC>;
    pdl_launch();                    // the PCG's next kernel may be staged while this grid drains
@@ -65,7 +62,6 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
    const int nel = min(NB, NE - eb);
    const bool active = (t < C::TA) && (e_loc < nel);
    const int ncols = nel*C::QQ;
-   auto eid = [&](int e) -> int { return LISTED ? __ldg(elist + eb + e) : eb + e; };   // element of local slot e
 
    // quadrature data of this thread's phase-B columns: issued first so that the DRAM
    // latency overlaps the gather and phase A
@@ -77,7 +73,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
       if (f < ncols)
       {
          const int e2 = f / C::QQ, col = f - e2*C::QQ;
-         const double *dptr = Dq + (size_t)eid(e2)*C::NQ + col;
+         const double *dptr = Dq + (size_t)(eb + e2)*C::NQ + col;
 #pragma unroll
          for (int qz = 0; qz < Q1D; qz++) { dq[k][qz] = __ldg(dptr + C::QQ*qz); }
       }
@@ -89,10 +85,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
    if (DIRECT_GATHER)
    {
       // only the restriction indices are staged; each slice thread gathers its own DD values
-      for (int it = t; it < nel*C::ND; it += C::T)
-      {
-         sIdx[(it / C::DD)*C::IDXS + it % C::DD] = LISTED ? __ldg(map + (size_t)eid(it / C::ND)*C::ND + it % C::ND) : __ldg(map + (size_t)eb*C::ND + it);
-      }
+      for (int it = t; it < nel*C::ND; it += C::T) { sIdx[(it / C::DD)*C::IDXS + it % C::DD] = __ldg(map + (size_t)eb*C::ND + it); }
    }
    else
    {
@@ -104,7 +97,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
       for (int k = 0; k < NIT; k++)
       {
          const int it = t + k*C::T;
-         id[k] = (it < nd) ? (LISTED ? __ldg(map + (size_t)eid(it / C::ND)*C::ND + it % C::ND) : __ldg(map + (size_t)eb*C::ND + it)) : 0;
+         id[k] = (it < nd) ? __ldg(map + (size_t)eb*C::ND + it) : 0;
       }
       double xv[NIT][NC];
 #pragma unroll
@@ -183,7 +176,7 @@ mass3d(const __grid_constant__ DevTables<D1D,Q1D> tab, const int NE, const int64
          const int kd = C::PREFETCH ? k : 0;
          if (!C::PREFETCH)
          {
-            const double *dptr = Dq + (size_t)eid(e2)*C::NQ + col;
+            const double *dptr = Dq + (size_t)(eb + e2)*C::NQ + col;
 #pragma unroll
             for (int qz = 0; qz < Q1D; qz++) { dq[0][qz] = __ldg(dptr + C::QQ*qz); }
          }

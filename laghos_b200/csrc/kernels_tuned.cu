@@ -6,7 +6,6 @@
 #include "device/mass3d_brick3.cuh"
 #include "device/staged3d.cuh"
 #include "device/mass3d_pencil.cuh"
-#include "device/mass3d_persist.cuh"
 
 namespace lagb {
 
@@ -42,57 +41,7 @@ struct TunedLaunch3D
       { int rc = set_smem(c, kern, Cfg::SMEM_BYTES); if (rc) { return rc; } }
       const int grid = (c.NE + NB - 1)/NB;
       if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
-      LAGB_LAUNCH_K(c, kern, grid, Cfg::T, Cfg::SMEM_BYTES, tab(c), c.NE, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y, c.d_part,
-                    (const int*)nullptr);
-      if (WITH_DEN) { c.dt_nblocks = grid; }
-      return LAGB_OK;
-   }
-   // the same kernel over an element list (part 0: elements touching shared dofs, part 1: the rest); the d^t A d
-   // partials of part 1 follow those of part 0, c.dt_nblocks accumulates over the two launches
-   template<int NC, bool WITH_DEN, int NB, int MINB>
-   static int mass_launch_list(Ctx &c, const double *x, double *y, int part)
-   {
-      using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
-      auto kern = tuned::mass3d<D1D,Q1D,NB,NC,WITH_DEN,MINB,true,true,true>;
-      { int rc = set_smem(c, kern, Cfg::SMEM_BYTES); if (rc) { return rc; } }
-      const int cnt = (part == 0) ? c.n_bnd_elems : c.NE - c.n_bnd_elems;
-      const int *list = c.d_elist + ((part == 0) ? 0 : c.n_bnd_elems);
-      const int grid = (cnt + NB - 1)/NB;
-      const int blk0 = (part == 0) ? 0 : c.dt_nblocks;
-      if (WITH_DEN && (blk0 + grid)*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
-      if (grid > 0)
-      {
-         LAGB_LAUNCH_K(c, kern, grid, Cfg::T, Cfg::SMEM_BYTES, tab(c), cnt, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y,
-                       c.d_part + (size_t)blk0*NC, list);
-      }
-      if (WITH_DEN) { c.dt_nblocks = blk0 + grid; }
-      return LAGB_OK;
-   }
-   static int mass_h1_part(Ctx &c, int nc, const double *x, double *y, bool with_den, int part)
-   {
-      if constexpr (D1D == 4)
-      {
-         if (nc == 3) { return with_den ? mass_launch_list<3,true,8,6>(c, x, y, part) : mass_launch_list<3,false,8,6>(c, x, y, part); }
-      }
-      set_error("mass3d: no listed variant for this order / component count"); return LAGB_ERR_INVALID;
-   }
-   template<int NC, bool WITH_DEN, int NB, int MINB>
-   static int mass_persist_launch(Ctx &c, const double *x, double *y)
-   {
-      using Cfg = tuned::Mass3DCfg<D1D,Q1D,NB,NC>;
-      auto kern = tuned::mass3d_persist<D1D,Q1D,NB,NC,WITH_DEN,MINB>;
-      const size_t bytes = Cfg::SMEM_BYTES + (size_t)NB*D1D*Cfg::IDXS*sizeof(int);    // second index buffer
-      { int rc = set_smem(c, kern, bytes); if (rc) { return rc; } }
-      int &occ = c.occ_cache[(const void*)kern];
-      if (occ == 0)
-      {
-         LAGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::T, bytes));
-         if (occ < 1) { set_error("mass3d_persist does not fit an SM"); return LAGB_ERR_STATE; }
-      }
-      const int nbatch = (c.NE + NB - 1)/NB;
-      const int grid = std::min(nbatch, c.num_sms*occ);
-      if (WITH_DEN && grid*NC > c.part_cap) { set_error("mass3d: partial buffer too small"); return LAGB_ERR_STATE; }
-      LAGB_LAUNCH_K(c, kern, grid, Cfg::T, bytes, tab(c), c.NE, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y, c.d_part);
+      LAGB_LAUNCH_K(c, kern, grid, Cfg::T, Cfg::SMEM_BYTES, tab(c), c.NE, (int64_t)c.ndofs, (const int*)c.d_map, (const double*)c.d_massD, x, y, c.d_part);
       if (WITH_DEN) { c.dt_nblocks = grid; }
       return LAGB_OK;
    }
@@ -107,8 +56,6 @@ struct TunedLaunch3D
             case 2: return mass_launch_v<NC,WITH_DEN,16,3,true,true>(c, x, y);
             case 3: return mass_launch_v<NC,WITH_DEN,8,5,true>(c, x, y);
             case 4: return mass_launch_v<NC,WITH_DEN,16,3,true>(c, x, y);
-            case 5: return mass_persist_launch<NC,WITH_DEN,8,6>(c, x, y);
-            case 6: return mass_persist_launch<NC,WITH_DEN,8,5>(c, x, y);
          }
          return mass_launch_v<NC,WITH_DEN,8,6,true,true>(c, x, y);   // measured best on B200 (profiles/microbench_r1_variants*.txt): 351 us
       }
@@ -541,7 +488,6 @@ struct TunedLaunch3D
    {
       ks.mass_h1 = &mass_h1; ks.qupdate = &qupdate; ks.force_mult = &force_mult;
       ks.force_mult_t = &force_mult_t; ks.mass_l2 = &mass_l2; ks.mass_brick = &mass_brick;
-      if (D1D == 4) { ks.mass_h1_part = &mass_h1_part; }
       ks.tuned_mass = true;
    }
 };
