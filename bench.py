@@ -65,11 +65,17 @@ def golden_e_norm(name, problem, rs, ok, step):
     if not os.path.exists(p):
         return None
     key = {("cube01", 1, 3): f"sedov_rs{rs}", ("cube01", 0, 3): f"tg_rs{rs}",
-           ("box01", 3, 2): f"tp_rs{rs}_ok2", ("box01", 3, 3): f"tp_rs{rs}_ok3"}.get((name, problem, ok))
+           ("box01", 3, 2): f"tp_rs{rs}_ok2", ("box01", 3, 3): f"tp_rs{rs}_ok3",
+           ("box01", 3, 4): f"tp_rs{rs}_ok4"}.get((name, problem, ok))
     ent = json.load(open(p)).get(key) if key else None
     if not ent:
         return None
-    return ent["e_norm_after_step"].get(str(step))
+    # `step` counts loop iterations; with rejected steps that differs from the history's step index
+    if str(step) in ent.get("e_norm_after_loops", {}):
+        return ent["e_norm_after_loops"][str(step)]
+    if ent.get("steps_run") == len(ent["e_norm_after_step"]):      # no step was rejected: loop count = step index
+        return ent["e_norm_after_step"].get(str(step))
+    return None
 
 
 class ClockSampler:
