@@ -98,6 +98,26 @@ const double *lagb_problem_qweights(const lagb_problem *p);       /* [NQ] */
 /* 1D tables: which = 0:B 1:G (H1, [q + Q1D*d]), 2:BL (L2 Bernstein, [q + Q1D*l]), 3:qx 4:qw */
 const double *lagb_problem_table(const lagb_problem *p, int which);
 
+/* Output files (host code, off the timed path): the reference's `-print` files
+ * <basename>_<ti>_mesh / _rho / _v / _e (laghos.cpp:873-900) and its VisIt data collection
+ * (laghos.cpp:866-871) in MFEM's text formats (mesh v1.0 with a `nodes` grid function, GridFunction::Save).
+ * H1 fields (mesh nodes, velocity) are written element-wise in L2_T1_<dim>D_P<ok> (discontinuous
+ * Gauss-Lobatto: exact for the path's H1 basis, independent of a reader's edge / face numbering), L2 fields
+ * (e, rho) in the path's own L2_T2_<dim>D_P<ot> layout.  All pointers are HOST pointers.
+ *   lagb_problem_write_mesh : h_x = H1 positions [dim*ndofs_h1] (NULL: the initial mesh)
+ *   lagb_problem_write_field: kind 0 = H1 field with vdim components [vdim*ndofs_h1], 1 = L2 scalar [ndofs_l2]
+ *   lagb_problem_write_print: the four `-print` files of step ti from the state S = (x | v | e) and rho
+ *   lagb_problem_write_visit: <collection>_<cycle:06d>/{mesh,Density,Velocity,Specific Internal Energy}.<rank:06d>
+ *                             and, on rank 0, <collection>_<cycle:06d>.mfem_root (h_rho may be NULL: no Density)
+ * A partitioned problem writes its own element block (a valid serial mesh of that block). */
+int lagb_problem_write_mesh(const lagb_problem *p, const double *h_x, const char *path, int precision);
+int lagb_problem_write_field(const lagb_problem *p, int kind, int vdim, const double *h_f, const char *path,
+                             int precision);
+int lagb_problem_write_print(const lagb_problem *p, const char *basename, int ti, const double *h_S,
+                             const double *h_rho, int precision);
+int lagb_problem_write_visit(const lagb_problem *p, const char *collection, int cycle, double time, double time_step,
+                             int rank, int nranks, const double *h_S, const double *h_rho, int precision);
+
 /* ------------------------------------------------------------------------- */
 /* Device context: the operators' shared state (QuadratureData and work        */
 /* vectors).  Replaces the members of LagrangianHydroOperator that the PA      */

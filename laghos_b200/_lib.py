@@ -41,7 +41,8 @@ class RunOptions(C.Structure):
                 ("batched_pcg", C.c_int), ("kernel_variant", C.c_int), ("device", C.c_int),
                 ("verbose", C.c_int), ("vis_steps", C.c_int), ("e2e_host_state", C.c_int),
                 ("warmup_steps", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("pgrid", C.c_int * 3),
-                ("nccl_id", C.c_void_p), ("profile_mass", C.c_int)]
+                ("nccl_id", C.c_void_p), ("profile_mass", C.c_int),
+                ("gfprint", C.c_int), ("visit", C.c_int), ("basename", C.c_char_p)]
 
 
 class RunResult(C.Structure):
@@ -72,7 +73,8 @@ lagb_memcpy_h2d_async lagb_memcpy_d2h lagb_memcpy_h2d_bg lagb_memcpy_d2h_bg lagb
 lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init lagb_allreduce_host
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
 lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set lagb_internal_energy lagb_kinetic_energy
-lagb_host_batch_plan_check lagb_compute_density lagb_pcg_vmass_all_x0""".split()
+lagb_host_batch_plan_check lagb_compute_density lagb_pcg_vmass_all_x0
+lagb_problem_write_mesh lagb_problem_write_field lagb_problem_write_print lagb_problem_write_visit""".split()
 
 
 def load_library():
@@ -110,6 +112,10 @@ def load_library():
     lib.lagb_problem_ess.restype = c_int_p
     lib.lagb_problem_table.argtypes = [vp, i32]
     lib.lagb_problem_table.restype = c_double_p
+    lib.lagb_problem_write_mesh.argtypes = [vp, vp, C.c_char_p, i32]
+    lib.lagb_problem_write_field.argtypes = [vp, i32, i32, vp, C.c_char_p, i32]
+    lib.lagb_problem_write_print.argtypes = [vp, C.c_char_p, i32, vp, vp, i32]
+    lib.lagb_problem_write_visit.argtypes = [vp, C.c_char_p, i32, dbl, dbl, i32, i32, vp, vp, i32]
     lib.lagb_ctx_create.argtypes = [C.POINTER(vp), C.POINTER(CtxDesc), vp]
     lib.lagb_ctx_destroy.argtypes = [vp]
     lib.lagb_ctx_sync.argtypes = [vp]

@@ -110,6 +110,36 @@ class Problem:
     def table(self, which, n):
         return self._arr(self.lib.lagb_problem_table(self.h, which), n, np.float64)
 
+    # ---- output files (reference -print / -visit, laghos.cpp:866-900); host arrays ----
+    @staticmethod
+    def _hp(a, n):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.size != n:
+            raise ValueError(f"expected {n} values, got {a.size}")
+        return a, a.ctypes.data_as(C.c_void_p)
+
+    def write_mesh(self, path, x=None, precision=8):
+        keep, px = self._hp(x, self.dim * self.ndofs_h1)
+        _check(self.lib, self.lib.lagb_problem_write_mesh(self.h, px, str(path).encode(), precision))
+
+    def write_field(self, path, f, kind, vdim=1, precision=8):
+        """kind 0: H1 field with vdim components [vdim*ndofs_h1]; kind 1: L2 scalar [ndofs_l2]"""
+        keep, pf = self._hp(f, vdim * self.ndofs_h1 if kind == 0 else self.ndofs_l2)
+        _check(self.lib, self.lib.lagb_problem_write_field(self.h, kind, vdim, pf, str(path).encode(), precision))
+
+    def write_print(self, basename, ti, S, rho, precision=8):
+        kS, pS = self._hp(S, self.s_size)
+        kr, pr = self._hp(rho, self.ndofs_l2)
+        _check(self.lib, self.lib.lagb_problem_write_print(self.h, str(basename).encode(), ti, pS, pr, precision))
+
+    def write_visit(self, collection, cycle, time, time_step, S, rho=None, rank=0, nranks=1, precision=8):
+        kS, pS = self._hp(S, self.s_size)
+        kr, pr = self._hp(rho, self.ndofs_l2)
+        _check(self.lib, self.lib.lagb_problem_write_visit(self.h, str(collection).encode(), cycle, time, time_step,
+                                                           rank, nranks, pS, pr, precision))
+
     def __del__(self):
         try:
             if getattr(self, "h", None):
@@ -310,7 +340,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
         ode_solver_type=4, t_final=0.6, max_tsteps=-1, cfl=0.5, cg_tol=1e-8, cg_max_iter=300,
         batched_pcg=True, kernel_variant=0, device=0, verbose=False, vis_steps=5, e2e_host_state=False,
         warmup_steps=0, rank=0, nranks=1, pgrid=(1, 1, 1), nccl_id=None, hist_cap=0, want_state=False,
-        profile_mass=False):
+        profile_mass=False, gfprint=False, visit=False, basename=None):
     """The reference driver's run (laghos.cpp main) through the C++ shim: lagb_laghos_run."""
     lib = load_library()
     dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
@@ -328,6 +358,10 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     o.verbose, o.vis_steps, o.e2e_host_state, o.warmup_steps = int(verbose), vis_steps, int(e2e_host_state), warmup_steps
     o.rank, o.nranks = rank, nranks
     o.profile_mass = int(profile_mass)
+    o.gfprint, o.visit = int(gfprint), int(visit)
+    base_b = None if basename is None else str(basename).encode()   # kept alive until the call returns
+    if base_b is not None:
+        o.basename = base_b
     for d in range(3):
         o.pgrid[d] = pgrid[d]
     idbuf = None

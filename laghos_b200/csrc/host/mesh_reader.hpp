@@ -6,7 +6,8 @@
 // with a message, like the reference aborts on unsupported input.
 //
 // Both vertex encodings that occur in data/ are read: the plain "vertices / N / dim / coordinates"
-// block and the "vertices / N / nodes / FiniteElementSpace ... (Linear | H1_*_P1)" grid function.
+// block and the "vertices / N / nodes / FiniteElementSpace ... (Linear | H1_*_P1)" grid function; so is the
+// element-wise "L2_T1_<dim>D_P<k>" nodes block that host/mesh_writer.hpp emits (corners -> vertices).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -82,12 +83,43 @@ inline bool read_mfem_mesh_rectilinear(const std::string &path, int &dim, std::v
       while (p < tok.size() && tok[p] != "Ordering:") { p++; }
       p++; if (!geti(ordering)) { err = "bad Ordering"; return false; }
       const bool linear = (fec == "Linear") || (fec.find("_P1") != std::string::npos && fec.rfind("H1_", 0) == 0);
-      if (!linear || vdim != dim) { err = "only linear (P1) nodal coordinates are supported: " + fec; return false; }
-      for (long i = 0; i < nv*dim; i++)
+      const std::string dg = "L2_T1_" + std::to_string(dim) + "D_P";    // element-wise Gauss-Lobatto (host/mesh_writer.hpp)
+      if (fec.rfind(dg, 0) == 0 && vdim == dim)
       {
-         double v; if (!getd(v)) { err = "truncated nodes"; return false; }
-         const long node = (ordering == 0) ? i % nv : i / dim, comp = (ordering == 0) ? i / nv : i % dim;
-         X[(size_t)node*dim + comp] = v;
+         // element-major, lexicographic inside an element: the corners give the vertex coordinates; the
+         // interior nodes are not checked (a deformed element fails the tensor-grid test below through its corners
+         // only if they moved: the reader is for initial / rectilinear meshes)
+         long k = 0;
+         try { k = std::stol(fec.substr(dg.size())); } catch (...) { k = 0; }
+         if (k < 1 || k > 16) { err = "bad nodes collection: " + fec; return false; }
+         long nd = 1; for (int a = 0; a < dim; a++) { nd *= k + 1; }
+         const long ntot = ne*nd;
+         std::vector<double> N((size_t)ntot*dim);
+         for (long i = 0; i < ntot*dim; i++)
+         {
+            double v; if (!getd(v)) { err = "truncated nodes"; return false; }
+            const long node = (ordering == 0) ? i % ntot : i / dim, comp = (ordering == 0) ? i / ntot : i % dim;
+            N[(size_t)node*dim + comp] = v;
+         }
+         static const int cq[4][2] = {{0,0},{1,0},{1,1},{0,1}};
+         for (long e = 0; e < ne; e++)
+            for (int c = 0; c < nvert_el; c++)
+            {
+               const long vtx = ev[(size_t)e*nvert_el + c];
+               if (vtx < 0 || vtx >= nv) { err = "vertex index out of range"; return false; }
+               const long loc = k*cq[c % 4][0] + (k + 1)*(k*cq[c % 4][1] + (k + 1)*(k*(long)(c / 4)));
+               for (int a = 0; a < dim; a++) { X[(size_t)vtx*dim + a] = N[(size_t)(e*nd + loc)*dim + a]; }
+            }
+      }
+      else
+      {
+         if (!linear || vdim != dim) { err = "only linear (P1) or element-wise L2_T1 nodal coordinates are supported: " + fec; return false; }
+         for (long i = 0; i < nv*dim; i++)
+         {
+            double v; if (!getd(v)) { err = "truncated nodes"; return false; }
+            const long node = (ordering == 0) ? i % nv : i / dim, comp = (ordering == 0) ? i / nv : i % dim;
+            X[(size_t)node*dim + comp] = v;
+         }
       }
    }
    else

@@ -3,6 +3,7 @@
 #include "host/problem.hpp"
 #include "host/partition.hpp"
 #include "host/mesh_reader.hpp"
+#include "host/mesh_writer.hpp"
 #include <string>
 
 namespace lagb { void set_error(const std::string &msg); }
@@ -127,6 +128,49 @@ const double *lagb_problem_table(const lagb_problem *p, int which)
       case 3: return p->P.tab.qx.data(); case 4: return p->P.tab.qw.data();
    }
    return nullptr;
+}
+
+// ---- output files (host/mesh_writer.hpp) ----
+static int writer_rc(bool ok, const std::string &err) { if (!ok) { lagb::set_error(err); return LAGB_ERR_INVALID; } return LAGB_OK; }
+
+int lagb_problem_write_mesh(const lagb_problem *p, const double *h_x, const char *path, int precision)
+{
+   if (!p || !path) { lagb::set_error("write_mesh: null argument"); return LAGB_ERR_INVALID; }
+   std::string err;
+   return writer_rc(lagb::write_text_file(path, err, [&](std::ostream &os)
+   { lagb::write_mfem_mesh(os, p->P, h_x, precision > 0 ? precision : 8); }), err);
+}
+
+int lagb_problem_write_field(const lagb_problem *p, int kind, int vdim, const double *h_f, const char *path, int precision)
+{
+   if (!p || !path || !h_f) { lagb::set_error("write_field: null argument"); return LAGB_ERR_INVALID; }
+   if (kind != 0 && kind != 1) { lagb::set_error("write_field: kind must be 0 (H1) or 1 (L2)"); return LAGB_ERR_INVALID; }
+   if (kind == 0 && vdim < 1) { lagb::set_error("write_field: vdim must be positive"); return LAGB_ERR_INVALID; }
+   if (kind == 1 && vdim != 1) { lagb::set_error("write_field: L2 fields are scalar"); return LAGB_ERR_INVALID; }
+   const int prec = precision > 0 ? precision : 8;
+   std::string err;
+   return writer_rc(lagb::write_text_file(path, err, [&](std::ostream &os)
+   {
+      if (kind == 0) { lagb::write_h1_field(os, p->P, h_f, vdim, prec); } else { lagb::write_l2_field(os, p->P, h_f, prec); }
+   }), err);
+}
+
+int lagb_problem_write_print(const lagb_problem *p, const char *basename, int ti, const double *h_S,
+                             const double *h_rho, int precision)
+{
+   if (!p || !basename || !h_S || !h_rho) { lagb::set_error("write_print: null argument"); return LAGB_ERR_INVALID; }
+   std::string err;
+   return writer_rc(lagb::write_print_files(p->P, basename, ti, h_S, h_rho, precision > 0 ? precision : 8, "", err), err);
+}
+
+int lagb_problem_write_visit(const lagb_problem *p, const char *collection, int cycle, double time, double time_step,
+                             int rank, int nranks, const double *h_S, const double *h_rho, int precision)
+{
+   if (!p || !collection || !h_S) { lagb::set_error("write_visit: null argument"); return LAGB_ERR_INVALID; }
+   if (rank < 0 || nranks < 1 || rank >= nranks || cycle < 0) { lagb::set_error("write_visit: bad rank / cycle"); return LAGB_ERR_INVALID; }
+   std::string err;
+   return writer_rc(lagb::write_visit_files(p->P, collection, cycle, time, time_step, rank, nranks, h_S, h_rho,
+                                            precision > 0 ? precision : 8, err), err);
 }
 
 } // extern "C"

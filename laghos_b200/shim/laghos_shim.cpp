@@ -3,6 +3,7 @@
 #include "laghos_shim.hpp"
 #include "../csrc/host/problem.hpp"
 #include "../csrc/host/partition.hpp"
+#include "../csrc/host/mesh_writer.hpp"
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -324,6 +325,7 @@ extern "C" void lagb_run_options_default(lagb_run_options *o)
    o->blast_scale = 0.125; o->ode_solver_type = 4; o->t_final = 0.6; o->max_tsteps = -1;
    o->cfl = 0.5; o->cg_tol = 1e-8; o->cg_max_iter = 300; o->batched_pcg = 1; o->vis_steps = 5;
    o->nranks = 1; o->pgrid[0] = o->pgrid[1] = o->pgrid[2] = 1;
+   o->basename = "results/Laghos";   // laghos.cpp:170
 }
 
 extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res, double *hist, int hist_cap, double *S_out)
@@ -464,6 +466,22 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
                res->e_norm = nrm; res->ti_last = ti;
                if (hist && n_hist < hist_cap) { hist[2*n_hist] = ti; hist[2*n_hist + 1] = nrm; n_hist++; }
                if (print && opt->rank == 0) { printf("step %5d,\tt = %5.4f,\tdt = %5.6f,\t|e| = %.10e\n", ti, t, dt, nrm); }
+            }
+            if ((opt->gfprint || opt->visit) && (last_step || (ti % std::max(1, opt->vis_steps)) == 0))
+            {
+               // laghos.cpp:845-900: density projected on the current mesh, then mesh + rho + v + e to files
+               Vector x_now, rho_gf(ctx, P.ndofs_l2);
+               x_now.MakeRef(S, 0, NV);
+               hydro.ComputeDensity(x_now, rho_gf);
+               std::vector<double> hS, hrho;
+               S.HostRead(hS); rho_gf.HostRead(hrho);
+               const std::string base = opt->basename ? opt->basename : "results/Laghos";
+               std::string err; char sfx[16] = "";
+               if (nranks > 1) { snprintf(sfx, sizeof sfx, ".%06d", opt->rank); }
+               bool ok = true;
+               if (opt->gfprint) { ok = lagb::write_print_files(P, base, ti, hS.data(), hrho.data(), 8, sfx, err); }
+               if (ok && opt->visit) { ok = lagb::write_visit_files(P, base, ti, t, dt, opt->rank, nranks, hS.data(), hrho.data(), 8, err); }
+               if (!ok) { LAGHOS_ABORT(err.c_str()); }
             }
          }
          if (opt->warmup_steps > 0 && steps == opt->warmup_steps)

@@ -262,6 +262,10 @@ typedef struct lagb_run_options
    int pgrid[3];
    const unsigned char *nccl_id; // 128 bytes from lagb_nccl_unique_id (rank 0), broadcast by the launcher
    int profile_mass;        // 1: CUDA-event timing of every H1 mass-apply launch (bench roofline)
+   // output files at every vis_steps-th accepted step and at the last one (laghos.cpp:845-900), off by default
+   int gfprint;             // -print: <basename>_<ti>_{mesh,rho,v,e} (per-rank suffix .<rank:06d> when nranks > 1)
+   int visit;               // -visit: <basename>_<ti:06d>.mfem_root + <basename>_<ti:06d>/<field>.<rank:06d>
+   const char *basename;    // -k, default "results/Laghos" (the directory must exist)
 } lagb_run_options;
 
 typedef struct lagb_run_result

@@ -1,0 +1,41 @@
+"""`-print` / `-visit` output of the driver loop on the GPU (reference laghos.cpp:845-900): at every vis_steps-th
+accepted step and at the last one the density is projected on the current mesh (device) and mesh + rho + v + e go
+to files through host/mesh_writer.hpp.  The files of the last step must hold the returned end state."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from test_mesh_writer import parse_gf, parse_mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def test_print_and_visit_files_of_a_run(built, tmp_path):
+    from laghos_b200.api import Problem, run
+    cfg = dict(mesh="cube01_hex", rs=1, problem=1, ok=2, ot=1)
+    base = str(tmp_path / "Laghos")
+    r = run(**cfg, t_final=10.0, max_tsteps=3, vis_steps=1, gfprint=True, visit=True, basename=base, want_state=True,
+            hist_cap=64)
+    P = Problem(**cfg)
+    S, nv, last = r["S"], P.dim * P.ndofs_h1, r["ti_last"]
+    written = sorted(int(f.split("_")[-2]) for f in os.listdir(tmp_path) if f.endswith("_mesh"))
+    assert written == [ti for ti, _ in r["hist"]] and written[-1] == last      # every accepted step (vis_steps 1)
+    M = parse_mesh(f"{base}_{last}_mesh")
+    assert M["fec"] == "L2_T1_3D_P2" and len(M["elems"]) == P.NE
+    assert np.allclose(M["nodes"].reshape(3, -1), S[:nv].reshape(3, -1)[:, P.h1_map], rtol=1e-7, atol=1e-12)
+    _, vdim, _, v = parse_gf(f"{base}_{last}_v")
+    assert vdim == 3 and np.allclose(v.reshape(3, -1), S[nv:2 * nv].reshape(3, -1)[:, P.h1_map], rtol=1e-7, atol=1e-12)
+    fec, _, _, e = parse_gf(f"{base}_{last}_e")
+    assert fec == "L2_T2_3D_P1" and np.allclose(e, S[2 * nv:], rtol=1e-7, atol=1e-12)
+    _, _, _, rho = parse_gf(f"{base}_{last}_rho")
+    assert rho.size == P.ndofs_l2 and np.all(np.isfinite(rho)) and rho.min() > 0.0
+    # mass is conserved: sum over the L2 dofs of the projected density stays near rho0 = 1 on average
+    assert abs(rho.mean() - 1.0) < 0.2
+    root = json.load(open(f"{base}_{last:06d}.mfem_root"))["dsets"]["main"]
+    assert root["cycle"] == last and root["domains"] == 1 and abs(root["time"] - r["t"]) < 1e-12
+    for f in list(root["fields"].values()) + [root["mesh"]]:
+        assert os.path.isfile(f["path"] % 0)
+    _, _, _, e2 = parse_gf(root["fields"]["Specific Internal Energy"]["path"] % 0)
+    assert np.array_equal(e2, e)
