@@ -301,7 +301,9 @@ int lagb_profile_mass(lagb_ctx *ctx, int enable);
 int lagb_profile_mass_get(lagb_ctx *ctx, double *seconds, int64_t *launches);
 /* kernel tuning knobs (tools/microbench.py): key 0 = launch variant of the legacy 3-component mass apply,
  * 1 = Force/Force^T, 2 = QUpdate, 3 = legacy 1-component mass, 4 = brick mass apply variant,
- * 5 = 1: no programmatic dependent launch between the colours, 6 = 1: legacy (atomic) mass path */
+ * 5 = 1: no programmatic dependent launch between the colours, 6 = mass-apply path (0 / 1: direct gather with
+ * atomic scatter, the default; 2 / 3: coloured brick kernels with a fixed summation order, measured slower),
+ * 10 = 1: the reference's global CG for the energy solve, 11 = 1: NCCL instead of peer-memory exchanges */
 int lagb_tune_set(lagb_ctx *ctx, int key, int value);
 /* HOST only (no CUDA call): builds the coloured brick schedule of the mass apply for the gather map
  * h_map [NE*ND] (grid = structured element grid hint or NULL, NB = elements per batch) and verifies
