@@ -98,6 +98,13 @@ const double *lagb_problem_qweights(const lagb_problem *p);       /* [NQ] */
 /* 1D tables: which = 0:B 1:G (H1, [q + Q1D*d]), 2:BL (L2 Bernstein, [q + Q1D*l]), 3:qx 4:qw */
 const double *lagb_problem_table(const lagb_problem *p, int which);
 
+/* End-of-run velocity error norms of the reference driver for problems 0 and 4 (laghos.cpp:970-982:
+ * ComputeMaxError / ComputeL1Error / ComputeL2Error against the initial velocity field, which is the exact solution
+ * there), from the HOST copy of the state S = (x | v | e): Gauss-Legendre rule of order 2 ok + 3 per element, exact
+ * field evaluated at the current position of each point.  out = { L_inf, L_1, L_2, sum of squares behind L_2 };
+ * a partitioned run reduces out[0] with max, out[1] and out[3] with sum, and takes L_2 = sqrt(out[3]). */
+int lagb_problem_velocity_error(const lagb_problem *p, const double *h_S, double out[4]);
+
 /* Output files (host code, off the timed path): the reference's `-print` files
  * <basename>_<ti>_mesh / _rho / _v / _e (laghos.cpp:873-900) and its VisIt data collection
  * (laghos.cpp:866-871) in MFEM's text formats (mesh v1.0 with a `nodes` grid function, GridFunction::Save).

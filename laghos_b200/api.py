@@ -110,6 +110,13 @@ class Problem:
     def table(self, which, n):
         return self._arr(self.lib.lagb_problem_table(self.h, which), n, np.float64)
 
+    def velocity_error(self, S):
+        """(L_inf, L_1, L_2) error of v against the initial (exact) velocity field: laghos.cpp:970-982, problems 0 / 4"""
+        keep, pS = self._hp(S, self.s_size)
+        out = (C.c_double * 4)()
+        _check(self.lib, self.lib.lagb_problem_velocity_error(self.h, pS, out))
+        return out[0], out[1], out[2]
+
     # ---- output files (reference -print / -visit, laghos.cpp:866-900); host arrays ----
     @staticmethod
     def _hp(a, n):
@@ -340,7 +347,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
         ode_solver_type=4, t_final=0.6, max_tsteps=-1, cfl=0.5, cg_tol=1e-8, cg_max_iter=300,
         batched_pcg=True, kernel_variant=0, device=0, verbose=False, vis_steps=5, e2e_host_state=False,
         warmup_steps=0, rank=0, nranks=1, pgrid=(1, 1, 1), nccl_id=None, hist_cap=0, want_state=False,
-        profile_mass=False, gfprint=False, visit=False, basename=None):
+        profile_mass=False, gfprint=False, visit=False, basename=None, v_error=False):
     """The reference driver's run (laghos.cpp main) through the C++ shim: lagb_laghos_run."""
     lib = load_library()
     dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
@@ -358,7 +365,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     o.verbose, o.vis_steps, o.e2e_host_state, o.warmup_steps = int(verbose), vis_steps, int(e2e_host_state), warmup_steps
     o.rank, o.nranks = rank, nranks
     o.profile_mass = int(profile_mass)
-    o.gfprint, o.visit = int(gfprint), int(visit)
+    o.gfprint, o.visit, o.v_error = int(gfprint), int(visit), int(v_error)
     base_b = None if basename is None else str(basename).encode()   # kept alive until the call returns
     if base_b is not None:
         o.basename = base_b
@@ -385,7 +392,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
                quad_tstep=r.timing.quad_tstep, wall_seconds=r.wall_seconds, device_seconds=r.device_seconds,
                mass_kernel_seconds=r.mass_kernel_seconds, mass_kernel_launches=r.mass_kernel_launches,
                mass_kernel_ncomp=r.mass_kernel_ncomp, work_mdof=r.work_mdof,
-               energy_init=r.energy_init, energy_final=r.energy_final,
+               energy_init=r.energy_init, energy_final=r.energy_final, v_err=list(r.v_err),
                h2d_bytes_per_step=r.h2d_bytes_per_step, d2h_bytes_per_step=r.d2h_bytes_per_step,
                kernel_launches=r.kernel_launches, ndofs_h1_global=r.ndofs_h1_global,
                ndofs_l2_global=r.ndofs_l2_global, ne_global=r.ne_global,

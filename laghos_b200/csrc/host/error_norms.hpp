@@ -1,0 +1,72 @@
+// End-of-run velocity error norms of the reference driver (laghos.cpp:970-982): for problems 0 and 4 the exact
+// velocity is constant in time, and the driver prints
+//    L_inf = v_gf.ComputeMaxError(v_coeff), L_1 = v_gf.ComputeL1Error(v_coeff), L_2 = v_gf.ComputeL2Error(v_coeff).
+// MFEM (not in the reference tree; restated from its published algorithm, GridFunction::ComputeLpError /
+// ComputeL2Error with a VectorCoefficient): per element the tensor Gauss-Legendre rule of order 2 p + 3
+// (p = the H1 order: p + 2 points per axis), at every point the Euclidean norm err = |v_h - v0(x_h)| with the exact
+// field evaluated at the CURRENT physical position x_h of the point, and
+//    L_inf = max err,   L_1 = sum w detJ err,   L_2 = sqrt(sum w detJ err^2).
+// Host code on the host copy of the state, off the timed path (diagnostics row 8f-2).  A partitioned run combines
+// the rank values with max / sum / sum of squares (ParGridFunction does the same reductions).
+#pragma once
+#include "problem.hpp"
+#include <cmath>
+#include <vector>
+
+namespace lagb {
+
+// out[0] = max, out[1] = L1 sum, out[2] = L2 sum of SQUARES (take the root after the rank reduction)
+inline void velocity_error_sums(const Problem &P, const double *S, double out[3])
+{
+   const int dim = P.dim, D = P.D1D, p = P.spec.ok, n = p + 2;    // IntRules.Get(geom, 2 p + 3): (2p+3)/2 + 1 points
+   std::vector<double> gx, gw;
+   gauss_legendre_01(n, gx, gw);
+   std::vector<double> B((size_t)n*D), G((size_t)n*D);
+   for (int q = 0; q < n; q++) { lagrange_eval(P.tab.gll, gx[q], &B[(size_t)q*D], &G[(size_t)q*D]); }
+   const int64_t nd = P.ndofs_h1;
+   const double *X = S, *V = S + P.h1_vsize();
+   ICs ic {P.spec.problem, dim};
+   const int nz = (dim == 3) ? n : 1, DZ = (dim == 3) ? D : 1;
+   double emax = 0.0, e1 = 0.0, e2 = 0.0;
+   for (int e = 0; e < P.NE; e++)
+   {
+      const int *map = &P.h1_map[(size_t)e*P.ND];
+      for (int qz = 0; qz < nz; qz++)
+         for (int qy = 0; qy < n; qy++)
+            for (int qx = 0; qx < n; qx++)
+            {
+               double x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+               for (int kz = 0; kz < DZ; kz++)
+                  for (int ky = 0; ky < D; ky++)
+                     for (int kx = 0; kx < D; kx++)
+                     {
+                        const double bx = B[(size_t)qx*D + kx], by = B[(size_t)qy*D + ky];
+                        const double bz = (dim == 3) ? B[(size_t)qz*D + kz] : 1.0;
+                        const double g[3] = {G[(size_t)qx*D + kx]*by*bz, bx*G[(size_t)qy*D + ky]*bz,
+                                             (dim == 3) ? bx*by*G[(size_t)qz*D + kz] : 0.0};
+                        const double b = bx*by*bz;
+                        const int64_t id = map[kx + D*(ky + D*kz)];
+                        for (int c = 0; c < dim; c++)
+                        {
+                           const double xc = X[(size_t)c*nd + id];
+                           x[c] += b*xc; v[c] += b*V[(size_t)c*nd + id];
+                           for (int d = 0; d < dim; d++) { J[c][d] += g[d]*xc; }
+                        }
+                     }
+               const double det = (dim == 2) ? J[0][0]*J[1][1] - J[0][1]*J[1][0]
+                                  : J[0][0]*(J[1][1]*J[2][2] - J[1][2]*J[2][1])
+                                  - J[0][1]*(J[1][0]*J[2][2] - J[1][2]*J[2][0])
+                                  + J[0][2]*(J[1][0]*J[2][1] - J[1][1]*J[2][0]);
+               double vex[3] = {0, 0, 0};
+               ic.v0(x, vex);
+               double err = 0.0;
+               for (int c = 0; c < dim; c++) { err += (v[c] - vex[c])*(v[c] - vex[c]); }
+               err = std::sqrt(err);
+               const double w = gw[qx]*gw[qy]*((dim == 3) ? gw[qz] : 1.0)*det;
+               emax = std::max(emax, err); e1 += w*err; e2 += w*err*err;
+            }
+   }
+   out[0] = emax; out[1] = e1; out[2] = e2;
+}
+
+} // namespace lagb

@@ -4,6 +4,7 @@
 #include "host/partition.hpp"
 #include "host/mesh_reader.hpp"
 #include "host/mesh_writer.hpp"
+#include "host/error_norms.hpp"
 #include <string>
 
 namespace lagb { void set_error(const std::string &msg); }
@@ -128,6 +129,15 @@ const double *lagb_problem_table(const lagb_problem *p, int which)
       case 3: return p->P.tab.qx.data(); case 4: return p->P.tab.qw.data();
    }
    return nullptr;
+}
+
+int lagb_problem_velocity_error(const lagb_problem *p, const double *h_S, double out[4])
+{
+   if (!p || !h_S || !out) { lagb::set_error("velocity_error: null argument"); return LAGB_ERR_INVALID; }
+   double s[3];
+   lagb::velocity_error_sums(p->P, h_S, s);
+   out[0] = s[0]; out[1] = s[1]; out[2] = std::sqrt(s[2]); out[3] = s[2];
+   return LAGB_OK;
 }
 
 // ---- output files (host/mesh_writer.hpp) ----

@@ -4,6 +4,7 @@
 #include "../csrc/host/problem.hpp"
 #include "../csrc/host/partition.hpp"
 #include "../csrc/host/mesh_writer.hpp"
+#include "../csrc/host/error_norms.hpp"
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -534,6 +535,17 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
       res->energy_final = hydro.InternalEnergy(e_gf0) + hydro.KineticEnergy(v_gf0);      // laghos.cpp:956-962
       if (opt->verbose && opt->rank == 0) { printf("\nEnergy  diff: %.2e\n", std::fabs(res->energy_init - res->energy_final)); }
       if (S_out) { std::vector<double> tmp; S.HostRead(tmp); memcpy(S_out, tmp.data(), sizeof(double)*N); }
+      if (opt->v_error && (opt->problem == 0 || opt->problem == 4))
+      {
+         // laghos.cpp:970-982: for problems 0 and 4 the exact velocity is constant in time
+         std::vector<double> hS; S.HostRead(hS);
+         double s[3];
+         lagb::velocity_error_sums(P, hS.data(), s);
+         if (nranks > 1) { LAGHOS_CHECK(lagb_allreduce_host(ctx, &s[0], 1, 2)); LAGHOS_CHECK(lagb_allreduce_host(ctx, &s[1], 2, 0)); }
+         res->v_err[0] = s[0]; res->v_err[1] = s[1]; res->v_err[2] = std::sqrt(s[2]);
+         if (opt->verbose && opt->rank == 0)
+         { printf("L_inf  error: %g\nL_1    error: %g\nL_2    error: %g\n", res->v_err[0], res->v_err[1], res->v_err[2]); }
+      }
       if (opt->verbose && opt->rank == 0)
       {
          printf("\nCG (H1) total time: %g\nCG (H1) rate (megadofs x cg_iterations / second): %g\n", times[0], res->fom[1]);

@@ -39,3 +39,16 @@ def test_print_and_visit_files_of_a_run(built, tmp_path):
         assert os.path.isfile(f["path"] % 0)
     _, _, _, e2 = parse_gf(root["fields"]["Specific Internal Energy"]["path"] % 0)
     assert np.array_equal(e2, e)
+
+
+def test_velocity_error_of_a_run(built):
+    """laghos.cpp:970-982: the driver's L_inf / L_1 / L_2 velocity errors (problems 0 and 4) are those of the end state"""
+    from laghos_b200.api import Problem, run
+    cfg = dict(mesh="square01_quad", rs=2, problem=0, ok=2, ot=1)
+    r = run(**cfg, t_final=10.0, max_tsteps=5, v_error=True, want_state=True)
+    assert np.allclose(r["v_err"], Problem(**cfg).velocity_error(r["S"]), rtol=1e-14)
+    assert 0 < r["v_err"][1] < r["v_err"][2] < r["v_err"][0] < 0.1     # smooth flow, a few steps: small errors
+    import pyoracle
+    ro = pyoracle.run(**cfg, t_final=10.0, max_tsteps=5, want_state=True)             # CPU oracle: same end state
+    assert np.allclose(r["v_err"], Problem(**cfg).velocity_error(ro["S"]), rtol=1e-7)
+    assert run(**dict(cfg, problem=1), t_final=10.0, max_tsteps=2, v_error=True)["v_err"] == [0.0, 0.0, 0.0]
