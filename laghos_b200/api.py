@@ -22,6 +22,15 @@ def _check(lib, rc):
         raise LagbError(lib.lagb_last_error().decode())
 
 
+def mesh_dim(mesh):
+    """dimension of a named mesh (data/ stems, hexbox_PxQxR, the reference's built-in `default[_2d | _NXxNY[xNZ]...]`)"""
+    if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D", "default_2d"):
+        return 2
+    if mesh.startswith("default_"):
+        return len(mesh.split("_")[1].split("x"))
+    return 3
+
+
 class Problem:
     """Host-side setup (mesh, tables, initial conditions): reference laghos.cpp:380-656."""
 
@@ -29,7 +38,7 @@ class Problem:
                  rank=0, pgrid=None, mesh_file=None, dim=None):
         self.lib = load_library()
         if dim is None:
-            dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
+            dim = mesh_dim(mesh)
         if blast_scale is None:
             blast_scale = 1.0 / 2 ** dim  # E0 = 1 (laghos.cpp:166, 603-604)
         self.args = dict(mesh=mesh, rs=rs, problem=problem, ok=ok, ot=ot, oq=oq, blast_scale=blast_scale,
@@ -350,7 +359,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
         profile_mass=False, gfprint=False, visit=False, basename=None, v_error=False):
     """The reference driver's run (laghos.cpp main) through the C++ shim: lagb_laghos_run."""
     lib = load_library()
-    dim = 2 if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D") else 3
+    dim = mesh_dim(mesh)
     if blast_scale is None:
         blast_scale = 1.0 / 2 ** dim
     o = RunOptions()

@@ -94,6 +94,40 @@ inline bool named_coarse_mesh(const std::string &name, int &dim,
       for (int d = 0; d < 3; d++) { for (int i = 0; i <= n[d]; i++) { coarse[d].push_back(0.5*i); } }
       return true;
    }
+   // the reference's built-in mesh (`-m default`, laghos.cpp:131-137, 427-447: Mesh::MakeCartesian2D/3D(nx, ny, nz, Sx, Sy,
+   // Sz) with boundary attribute k on the faces of constant x_{k-1}): "default" = -dim 3 -nx 2 -ny 2 -nz 2 on the unit
+   // cube (the mesh of the --checks table, = cube01_hex), "default_2d" = -dim 2 (= square01_quad), and
+   // "default_<nx>x<ny>[x<nz>][_S<Sx>x<Sy>[x<Sz>]]" for -nx/-ny/-nz and -Sx/-Sy/-Sz
+   if (name.rfind("default", 0) == 0)
+   {
+      int n[3] = {2, 2, 2}; double S[3] = {1.0, 1.0, 1.0};
+      dim = 3;
+      const std::string rest = name.substr(7);
+      if (rest == "_2d") { dim = 2; }
+      else if (!rest.empty())
+      {
+         char tail[64] = "";
+         int a = 0, b = 0, c = 0;
+         const int got = sscanf(rest.c_str(), "_%dx%dx%d%63s", &a, &b, &c, tail);
+         if (got >= 3) { dim = 3; n[0] = a; n[1] = b; n[2] = c; }
+         else if (sscanf(rest.c_str(), "_%dx%d%63s", &a, &b, tail) >= 2) { dim = 2; n[0] = a; n[1] = b; }
+         else { return false; }
+         if (tail[0] != 0)
+         {
+            double sx = 0, sy = 0, sz = 0; char junk = 0;
+            if (dim == 3) { if (sscanf(tail, "_S%lfx%lfx%lf%c", &sx, &sy, &sz, &junk) != 3) { return false; } }
+            else { sz = 1.0; if (sscanf(tail, "_S%lfx%lf%c", &sx, &sy, &junk) != 2) { return false; } }
+            if (!(sx > 0 && sy > 0 && sz > 0)) { return false; }
+            S[0] = sx; S[1] = sy; S[2] = sz;
+         }
+      }
+      for (int d = 0; d < dim; d++)
+      {
+         if (n[d] < 1 || n[d] > 4096) { return false; }
+         for (int i = 0; i <= n[d]; i++) { coarse[d].push_back(i == n[d] ? S[d] : S[d]*i/n[d]); }
+      }
+      return true;
+   }
    return false;
 }
 

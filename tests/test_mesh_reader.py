@@ -107,3 +107,22 @@ def test_reference_data_files_match_named_meshes(built, name, dim):
     for a in range(dim):
         assert np.array_equal(A.mesh_breaks(a), B.mesh_breaks(a)), (name, a, A.mesh_breaks(a), B.mesh_breaks(a))
     assert np.array_equal(A.S0, B.S0) and np.array_equal(A.h1_map, B.h1_map)
+
+
+def test_builtin_default_mesh(built):
+    """reference `-m default` (laghos.cpp:131-137, 427-447): MakeCartesian(nx, ny, nz; Sx, Sy, Sz), the mesh of --checks"""
+    from laghos_b200.api import LagbError, Problem, mesh_dim
+    a, b = Problem(mesh="default", rs=1, problem=1), Problem(mesh="cube01_hex", rs=1, problem=1)
+    assert np.array_equal(a.S0, b.S0) and np.array_equal(a.h1_map, b.h1_map)
+    a, b = Problem(mesh="default_2d", rs=2, problem=0), Problem(mesh="square01_quad", rs=2, problem=0)
+    assert a.dim == 2 and np.array_equal(a.S0, b.S0)
+    c = Problem(mesh="default_4x3x2_S2x1.5x0.5", rs=0, problem=1)
+    assert c.dim == 3 and c.NE == 24
+    assert np.allclose(c.mesh_breaks(0), np.linspace(0, 2, 5)) and np.allclose(c.mesh_breaks(1), np.linspace(0, 1.5, 4))
+    assert np.allclose(c.mesh_breaks(2), [0, 0.25, 0.5])
+    d = Problem(mesh="default_3x5", rs=0, problem=0)
+    assert d.dim == 2 and d.NE == 15 and mesh_dim("default_3x5_S2x1") == 2
+    assert np.allclose(Problem(mesh="default_3x5_S2x1", rs=0, problem=0).mesh_breaks(0), [0, 2 / 3, 4 / 3, 2])
+    for bad in ("default_0x2", "default_2x2_S0x1", "default_2x2x2_Sax1x1", "defaultx"):
+        with pytest.raises(LagbError):
+            Problem(mesh=bad, rs=0, problem=1, dim=3)
