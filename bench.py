@@ -135,43 +135,63 @@ def peaks():
 REF_RS = 4   # the CPU arm always runs cube01_hex -p 1 -rs 4 -ok 3 -ot 2 (32^3 elements): one fixed configuration
 
 
-def cpu_oracle_run(threads, steps, rs=REF_RS, warm=True):
+def cpu_oracle_run(threads, steps, rs=REF_RS, warm=2, mesh="cube01_hex", problem=1, ok=3):
     """The reference's CPU -pa algorithm (oracle port, element-parallel over `threads` host threads, the
-    stand-in for `mpirun -np <cores> laghos`) on a FIXED sample of the same workload: same problem and
-    orders at -rs `rs`, `steps` RK4 steps from t = 0 after a discarded 2-step warm-up run (thread start-up,
+    stand-in for `mpirun -np <cores> laghos`) on a FIXED sample of the same workload: same mesh, problem and
+    orders at -rs `rs`, `steps` RK4 steps from t = 0 after a discarded `warm`-step warm-up run (thread start-up,
     page faults).  Rates are per dof, so they compare across -rs.  Returns (rate, sample, seconds, result)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
-    kw = dict(mesh="cube01_hex", problem=1, ok=3, ot=2, t_final=1e9, cg_tol=1e-8, nthreads=threads, rs=rs)
+    kw = dict(mesh=mesh, problem=problem, ok=ok, ot=ok - 1, t_final=1e9, cg_tol=1e-8, nthreads=threads, rs=rs)
     if warm:
-        pyoracle.run(max_tsteps=1, **kw)
+        pyoracle.run(max_tsteps=int(warm) - 1, **kw)
     t0 = time.time()
     r = pyoracle.run(max_tsteps=steps - 1, **kw)
     el = time.time() - t0
     sample = (f"oracle port (reference serial -pa algorithm, {threads} element-parallel host threads), "
-              f"cube01_hex -p 1 -rs {rs} -ok 3 -ot 2, {r['steps']} RK4 steps from t=0, {el:.1f} s wall")
+              f"{mesh} -p {problem} -rs {rs} -ok {ok} -ot {ok - 1}, {r['steps']} RK4 steps from t=0, {el:.1f} s wall")
     return r["fom"][0], sample, el, r
+
+
+def job_sizes(n_gpus, rs, name, ok):
+    """(elements per GPU, global H1 dofs, global L2 dofs) of the N-GPU workload: N blocks of COARSE x 2^rs elements"""
+    pg = PGRIDS[n_gpus]
+    nel = [c * 2 ** rs for c in COARSE[name]]
+    gl = [nel[d] * pg[d] for d in range(3)]
+    h1 = (ok * gl[0] + 1) * (ok * gl[1] + 1) * (ok * gl[2] + 1)
+    return nel[0] * nel[1] * nel[2], h1, gl[0] * gl[1] * gl[2] * ok ** 3
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the
-    reference binary cannot be built here: MFEM/MPI/hypre absent).  Fixed configuration
-    (-rs 4, all host threads, --steps steps after a 2-step warm-up run) so that two boxes with the same
-    core count report the same number."""
+    reference binary cannot be built here: MFEM/MPI/hypre absent) on the native arm's metric and
+    config.  Each run is a bounded sample of that workload: the same mesh, problem and orders one refinement level
+    down (-rs 4 for the -rs 5 job: 1/8 of one GPU's elements), all host threads, --steps steps after a discarded
+    --warmup-step run; the metric is a rate per dof, so it compares across -rs.  The sample does not depend on the host's
+    speed, so two boxes with the same core count report the same number."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     steps = max(args.steps, 1)
-    fom, sample, el, r = cpu_oracle_run(threads, steps)
+    mesh = "cube01_hex" if args.workload == "cube01" else "box01_hex"
+    ref_rs = REF_RS if args.workload == "cube01" else REF_RS - 1
+    warm = max(args.warmup, 1)
+    fom, sample, el, r = cpu_oracle_run(threads, steps, rs=ref_rs, warm=warm, mesh=mesh, problem=args.problem, ok=args.ok)
     T = r["t_cgH1"] + r["t_force"] + r["t_qdata"]
     work = fom * T
+    _, pg, wl_name = workload(args.gpus, args.rs, args.workload, args.problem, args.ok)
+    ne_gpu, h1, l2 = job_sizes(args.gpus, args.rs, args.workload, args.ok)
+    metric = METRIC if (args.problem, args.ok) == (1, 3) else \
+        f"Mdof x steps / s (major kernels total rate), 3D {PROBLEM_NAMES.get(args.problem, args.problem)} Q{args.ok}/Q{args.ok - 1} -pa"
     line = {
-        "impl": "reference", "metric": METRIC, "value": fom, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": r["steps"], "warmup": 2, "ms_per_step": 1e3 * el / max(r["steps"], 1), "higher_is_better": True,
+        "impl": "reference", "metric": metric, "value": fom, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": warm, "ms_per_step": 1e3 * el / max(r["steps"], 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cube01_hex -p 1 -rs {REF_RS} -ok 3 -ot 2 -pa (fixed CPU sample of the GPU arm's "
-                               f"-rs {args.rs} workload; rates are per dof so they compare)",
-                   "cg_tol": 1e-8, "ode": "RK4", "host_threads": threads},
+        # the native arm's config (same keys, same values); the bounded sample actually run is in cpu_baseline.sample
+        "config": {"workload": wl_name, "elements_per_gpu": ne_gpu, "h1_dofs_global": h1, "l2_dofs_global": l2,
+                   "ode": "RK4", "cg_tol": 1e-8, "parallelism": f"element blocks {pg[0]}x{pg[1]}x{pg[2]}",
+                   "sample": f"{mesh} -p {args.problem} -rs {ref_rs} -ok {args.ok} -ot {args.ok - 1} -pa on the host "
+                             f"(rate per dof)", "host_threads": threads},
         "cpu_baseline": {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": work / el, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -328,11 +348,11 @@ def main():
             line["roofline"]["traffic"] = None          # the committed ncu capture is of the Q3Q2 kernel
         if not args.no_cpu and args.gpus == 1:
             threads = os.cpu_count() or 1
-            fom, sample, el4, _ = cpu_oracle_run(threads, steps=2, warm=False)
+            fom, sample, el4, _ = cpu_oracle_run(threads, steps=2, warm=0)
             line["cpu_baseline"] = {"value": fom, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
             if el4 < 6.0:
                 # one more leg on the BASELINE size itself (-rs 5) when the host has the cores for it (~8x the work)
-                fom5, sample5, _, _ = cpu_oracle_run(threads, steps=1, rs=5, warm=False)
+                fom5, sample5, _, _ = cpu_oracle_run(threads, steps=1, rs=5, warm=0)
                 line["cpu_baseline"]["rs5"] = {"value": fom5, "sample": sample5}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -43,3 +43,18 @@ def test_reference_arm_is_a_fixed_configuration():
     assert b.REF_RS == 4
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert "budget_s" not in src          # no wall-time-driven choice of the CPU sample size any more
+
+
+def test_reference_arm_reports_the_native_config():
+    """--impl reference prints the native arm's config (workload name, sizes); the bounded CPU sample is named
+    beside it.  Sizes against the native line of profiles/bench_r2_1gpu.json and the 8-GPU job (cube01_hex -rs 6)."""
+    b = _bench()
+    assert b.job_sizes(1, 5, "cube01", 3) == (262144, 7189057, 7077888)
+    assert b.job_sizes(8, 5, "cube01", 3) == (262144, 385 ** 3, 128 ** 3 * 27)
+    assert b.job_sizes(1, 4, "box01", 2) == (65536, 129 * 65 * 65, 65536 * 8)
+    native = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_1gpu.json")))["config"]
+    ne, h1, l2 = b.job_sizes(1, 5, "cube01", 3)
+    assert (native["elements_per_gpu"], native["h1_dofs_global"], native["l2_dofs_global"]) == (ne, h1, l2)
+    assert b.workload(1, 5)[2] == native["workload"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert '"config": {"workload": wl_name, "elements_per_gpu": ne_gpu' in src      # the reference line uses them
