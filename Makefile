@@ -32,6 +32,14 @@ oracle/_build/oracle_cli: oracle/oracle_main.cpp oracle/laghos_oracle.hpp oracle
 	@mkdir -p oracle/_build
 	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -o $@ oracle/oracle_main.cpp -lpthread
 
+# the reference's own Sedov exact solution (self-contained: sedov_sol.cpp + two headers, no MFEM), compiled from the
+# sources where they lie; only where /root/reference exists (this container), output into oracle/_ref/ (git-ignored)
+REF_SEDOV = /root/reference/sedov
+oracle/_ref/libsedov_ref.so: oracle/sedov_ref_capi.cpp
+	@mkdir -p oracle/_ref
+	$(CXX) -O2 -std=c++17 -fPIC -shared -I$(REF_SEDOV) -o $@ oracle/sedov_ref_capi.cpp $(REF_SEDOV)/sedov_sol.cpp
+ref: $(if $(wildcard $(REF_SEDOV)/sedov_sol.cpp),oracle/_ref/libsedov_ref.so)
+
 clean:
 	rm -rf build laghos_b200/lib oracle/_build
-.PHONY: all clean
+.PHONY: all clean ref

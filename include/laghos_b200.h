@@ -105,6 +105,19 @@ const double *lagb_problem_table(const lagb_problem *p, int which);
  * a partitioned run reduces out[0] with max, out[1] and out[3] with sum, and takes L_2 = sqrt(out[3]). */
 int lagb_problem_velocity_error(const lagb_problem *p, const double *h_S, double out[4]);
 
+/* `-err` of the reference driver (laghos.cpp:1009-1085, problem 1 on the built-in mesh): the exact Taylor - von Neumann
+ * - Sedov solution (own restatement of the published similarity solution, host/sedov_exact.hpp; the reference uses
+ * sedov/sedov_sol.cpp) and the L2 error of the density field against it.
+ *   lagb_sedov_exact_eval: rho, v, p at n radii at time t; alpha_override > 0 replaces the energy integral;
+ *                          info = { alpha, r2, U, rho2, v2, p2 }
+ *   lagb_problem_sedov_density_error: h_S = host state (positions used), h_rho = ComputeDensity field [ndofs_l2],
+ *                          gamma / rho0 / blast_energy as the driver passes them (1.4, 1, E0);
+ *                          out = { L2 error, sum of squares } (partitioned runs add out[1] and take the root) */
+int lagb_sedov_exact_eval(int dim, double gamma, double rho0, double blast_energy, double t, double alpha_override,
+                          int n, const double *r, double *rho, double *v, double *p, double info[6]);
+int lagb_problem_sedov_density_error(const lagb_problem *p, const double *h_S, const double *h_rho, double t,
+                                     double gamma, double rho0, double blast_energy, double out[2]);
+
 /* Output files (host code, off the timed path): the reference's `-print` files
  * <basename>_<ti>_mesh / _rho / _v / _e (laghos.cpp:873-900) and its VisIt data collection
  * (laghos.cpp:866-871) in MFEM's text formats (mesh v1.0 with a `nodes` grid function, GridFunction::Save).

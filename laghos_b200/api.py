@@ -22,6 +22,17 @@ def _check(lib, rc):
         raise LagbError(lib.lagb_last_error().decode())
 
 
+def sedov_exact(dim, t, r, gamma=1.4, rho0=1.0, blast_energy=1.0, alpha=0.0):
+    """exact Sedov blast wave at radii r: (rho, v, p, info = [alpha, r2, U, rho2, v2, p2]); host/sedov_exact.hpp"""
+    lib = load_library()
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    rho, v, p, info = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r), np.zeros(6)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib, lib.lagb_sedov_exact_eval(dim, gamma, rho0, blast_energy, t, alpha, r.size, vp(r), vp(rho), vp(v), vp(p),
+                                          vp(info)))
+    return rho, v, p, info
+
+
 def mesh_dim(mesh):
     """dimension of a named mesh (data/ stems, hexbox_PxQxR, the reference's built-in `default[_2d | _NXxNY[xNZ]...]`)"""
     if mesh in ("square01_quad", "rectangle01_quad", "square_gresho", "rt2D", "default_2d"):
@@ -125,6 +136,14 @@ class Problem:
         out = (C.c_double * 4)()
         _check(self.lib, self.lib.lagb_problem_velocity_error(self.h, pS, out))
         return out[0], out[1], out[2]
+
+    def sedov_density_error(self, S, rho, t, gamma=1.4, rho0=1.0, blast_energy=1.0):
+        """`-err`: L2 error of the density field against the exact Sedov solution at time t (laghos.cpp:1009-1085)"""
+        kS, pS = self._hp(S, self.s_size)
+        kr, pr = self._hp(rho, self.ndofs_l2)
+        out = (C.c_double * 2)()
+        _check(self.lib, self.lib.lagb_problem_sedov_density_error(self.h, pS, pr, t, gamma, rho0, blast_energy, out))
+        return out[0]
 
     # ---- output files (reference -print / -visit, laghos.cpp:866-900); host arrays ----
     @staticmethod
@@ -356,7 +375,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
         ode_solver_type=4, t_final=0.6, max_tsteps=-1, cfl=0.5, cg_tol=1e-8, cg_max_iter=300,
         batched_pcg=True, kernel_variant=0, device=0, verbose=False, vis_steps=5, e2e_host_state=False,
         warmup_steps=0, rank=0, nranks=1, pgrid=(1, 1, 1), nccl_id=None, hist_cap=0, want_state=False,
-        profile_mass=False, gfprint=False, visit=False, basename=None, v_error=False):
+        profile_mass=False, gfprint=False, visit=False, basename=None, v_error=False, check_exact_sedov=False):
     """The reference driver's run (laghos.cpp main) through the C++ shim: lagb_laghos_run."""
     lib = load_library()
     dim = mesh_dim(mesh)
@@ -375,6 +394,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     o.rank, o.nranks = rank, nranks
     o.profile_mass = int(profile_mass)
     o.gfprint, o.visit, o.v_error = int(gfprint), int(visit), int(v_error)
+    o.check_exact_sedov = int(check_exact_sedov)
     base_b = None if basename is None else str(basename).encode()   # kept alive until the call returns
     if base_b is not None:
         o.basename = base_b
@@ -401,7 +421,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
                quad_tstep=r.timing.quad_tstep, wall_seconds=r.wall_seconds, device_seconds=r.device_seconds,
                mass_kernel_seconds=r.mass_kernel_seconds, mass_kernel_launches=r.mass_kernel_launches,
                mass_kernel_ncomp=r.mass_kernel_ncomp, work_mdof=r.work_mdof,
-               energy_init=r.energy_init, energy_final=r.energy_final, v_err=list(r.v_err),
+               energy_init=r.energy_init, energy_final=r.energy_final, v_err=list(r.v_err), density_l2_err=r.density_l2_err,
                h2d_bytes_per_step=r.h2d_bytes_per_step, d2h_bytes_per_step=r.d2h_bytes_per_step,
                kernel_launches=r.kernel_launches, ndofs_h1_global=r.ndofs_h1_global,
                ndofs_l2_global=r.ndofs_l2_global, ne_global=r.ne_global,

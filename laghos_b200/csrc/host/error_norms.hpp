@@ -10,6 +10,7 @@
 // the rank values with max / sum / sum of squares (ParGridFunction does the same reductions).
 #pragma once
 #include "problem.hpp"
+#include "sedov_exact.hpp"
 #include <cmath>
 #include <vector>
 
@@ -67,6 +68,74 @@ inline void velocity_error_sums(const Problem &P, const double *S, double out[3]
             }
    }
    out[0] = emax; out[1] = e1; out[2] = e2;
+}
+
+// `-err` of the reference driver (laghos.cpp:1009-1085): L2 error of the density against the exact Sedov solution at
+// time t.  rho = the L2 (Bernstein) density field of ComputeDensity on the current mesh x = S[0 : dim ndofs]; rule
+// IntRules.Get(geom, err_order), err_order = 2 max(2 (max(ok, ot) + 1), oq), i.e. err_order/2 + 1 Gauss points per
+// axis; at every point (rho_exact(|x_q - 0|) - rho_h(x_q))^2 weighted with w detJ (QuadratureFunction::Integrate).
+// Returns the sum of squares of this rank's elements (root after the rank reduction).
+inline double sedov_density_error_sum(const Problem &P, const double *S, const double *rho, const SedovExact &sol)
+{
+   const int dim = P.dim, D = P.D1D, L1 = P.L1D;
+   const int err_order = 2*std::max(2*(std::max(P.spec.ok, P.spec.ot) + 1), P.spec.oq);
+   const int n = err_order/2 + 1;
+   std::vector<double> gx, gw;
+   gauss_legendre_01(n, gx, gw);
+   std::vector<double> B((size_t)n*D), G((size_t)n*D), BL((size_t)n*L1);
+   for (int q = 0; q < n; q++)
+   {
+      lagrange_eval(P.tab.gll, gx[q], &B[(size_t)q*D], &G[(size_t)q*D]);
+      bernstein_eval(L1 - 1, gx[q], &BL[(size_t)q*L1]);
+   }
+   const int64_t nd = P.ndofs_h1;
+   const int nz = (dim == 3) ? n : 1, DZ = (dim == 3) ? D : 1, LZ = (dim == 3) ? L1 : 1;
+   double sum = 0.0;
+   for (int e = 0; e < P.NE; e++)
+   {
+      const int *map = &P.h1_map[(size_t)e*P.ND];
+      const double *re = rho + (size_t)e*P.NL;
+      for (int qz = 0; qz < nz; qz++)
+         for (int qy = 0; qy < n; qy++)
+            for (int qx = 0; qx < n; qx++)
+            {
+               double x[3] = {0, 0, 0}, J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+               for (int kz = 0; kz < DZ; kz++)
+                  for (int ky = 0; ky < D; ky++)
+                     for (int kx = 0; kx < D; kx++)
+                     {
+                        const double bx = B[(size_t)qx*D + kx], by = B[(size_t)qy*D + ky];
+                        const double bz = (dim == 3) ? B[(size_t)qz*D + kz] : 1.0;
+                        const double g[3] = {G[(size_t)qx*D + kx]*by*bz, bx*G[(size_t)qy*D + ky]*bz,
+                                             (dim == 3) ? bx*by*G[(size_t)qz*D + kz] : 0.0};
+                        const int64_t id = map[kx + D*(ky + D*kz)];
+                        for (int c = 0; c < dim; c++)
+                        {
+                           const double xc = S[(size_t)c*nd + id];
+                           x[c] += bx*by*bz*xc;
+                           for (int d = 0; d < dim; d++) { J[c][d] += g[d]*xc; }
+                        }
+                     }
+               double rh = 0.0;
+               for (int lz = 0; lz < LZ; lz++)
+                  for (int ly = 0; ly < L1; ly++)
+                     for (int lx = 0; lx < L1; lx++)
+                     {
+                        rh += BL[(size_t)qx*L1 + lx]*BL[(size_t)qy*L1 + ly]*((dim == 3) ? BL[(size_t)qz*L1 + lz] : 1.0)
+                              *re[lx + L1*(ly + L1*lz)];
+                     }
+               const double det = (dim == 2) ? J[0][0]*J[1][1] - J[0][1]*J[1][0]
+                                  : J[0][0]*(J[1][1]*J[2][2] - J[1][2]*J[2][1])
+                                  - J[0][1]*(J[1][0]*J[2][2] - J[1][2]*J[2][0])
+                                  + J[0][2]*(J[1][0]*J[2][1] - J[1][1]*J[2][0]);
+               const double r = std::sqrt(x[0]*x[0] + x[1]*x[1] + x[2]*x[2]);
+               double rex, vex, pex;
+               sol.eval(r, rex, vex, pex);
+               const double w = gw[qx]*gw[qy]*((dim == 3) ? gw[qz] : 1.0)*det;
+               sum += w*(rex - rh)*(rex - rh);
+            }
+   }
+   return sum;
 }
 
 } // namespace lagb

@@ -140,6 +140,37 @@ int lagb_problem_velocity_error(const lagb_problem *p, const double *h_S, double
    return LAGB_OK;
 }
 
+int lagb_sedov_exact_eval(int dim, double gamma, double rho0, double blast_energy, double t, double alpha_override,
+                          int n, const double *r, double *rho, double *v, double *pr, double info[6])
+{
+   try
+   {
+      if (!(t > 0) || n < 0 || (n > 0 && (!r || !rho || !v || !pr))) { lagb::set_error("sedov_exact_eval: bad argument"); return LAGB_ERR_INVALID; }
+      lagb::SedovExact s(dim, gamma, rho0, blast_energy);
+      if (alpha_override > 0) { s.set_alpha(alpha_override); }
+      s.set_time(t);
+      for (int i = 0; i < n; i++) { s.eval(r[i], rho[i], v[i], pr[i]); }
+      if (info) { info[0] = s.alpha; info[1] = s.r2; info[2] = s.U; info[3] = s.rho2; info[4] = s.v2; info[5] = s.p2; }
+      return LAGB_OK;
+   }
+   catch (const std::exception &e) { lagb::set_error(e.what()); return LAGB_ERR_INVALID; }
+}
+
+int lagb_problem_sedov_density_error(const lagb_problem *p, const double *h_S, const double *h_rho, double t,
+                                     double gamma, double rho0, double blast_energy, double out[2])
+{
+   try
+   {
+      if (!p || !h_S || !h_rho || !out || !(t > 0)) { lagb::set_error("sedov_density_error: bad argument"); return LAGB_ERR_INVALID; }
+      lagb::SedovExact s(p->P.dim, gamma, rho0, blast_energy);
+      s.set_time(t);
+      out[1] = lagb::sedov_density_error_sum(p->P, h_S, h_rho, s);
+      out[0] = std::sqrt(out[1]);
+      return LAGB_OK;
+   }
+   catch (const std::exception &e) { lagb::set_error(e.what()); return LAGB_ERR_INVALID; }
+}
+
 // ---- output files (host/mesh_writer.hpp) ----
 static int writer_rc(bool ok, const std::string &err) { if (!ok) { lagb::set_error(err); return LAGB_ERR_INVALID; } return LAGB_OK; }
 

@@ -535,6 +535,26 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
       res->energy_final = hydro.InternalEnergy(e_gf0) + hydro.KineticEnergy(v_gf0);      // laghos.cpp:956-962
       if (opt->verbose && opt->rank == 0) { printf("\nEnergy  diff: %.2e\n", std::fabs(res->energy_init - res->energy_final)); }
       if (S_out) { std::vector<double> tmp; S.HostRead(tmp); memcpy(S_out, tmp.data(), sizeof(double)*N); }
+      if (opt->check_exact_sedov)
+      {
+         // -err (laghos.cpp:1009-1085): density projected on the final mesh against the exact Sedov solution at time t
+         // (gamma = 1.4, rho0 = 1, omega = 0, blast at the origin)
+         if (opt->problem != 1) { LAGHOS_ABORT("Can only compare problem 1 (Sedov) against the exact solution"); }
+         lagb::SedovExact asol(P.dim, 1.4, 1.0, opt->blast_scale*(1 << P.dim));
+         asol.set_time(t);
+         double min_r = 1e300;
+         for (int dd = 0; dd < P.dim; dd++) { min_r = std::min(min_r, gm.brk[dd].back()); }
+         if (!(asol.r2 <= min_r)) { LAGHOS_ABORT("Solution reflections off boundaries detected, cannot compare against exact solution."); }
+         Vector x_now, rho_gf(ctx, P.ndofs_l2);
+         x_now.MakeRef(S, 0, NV);
+         hydro.ComputeDensity(x_now, rho_gf);
+         std::vector<double> hS, hrho;
+         S.HostRead(hS); rho_gf.HostRead(hrho);
+         double sum = lagb::sedov_density_error_sum(P, hS.data(), hrho.data(), asol);
+         if (nranks > 1) { LAGHOS_CHECK(lagb_allreduce_host(ctx, &sum, 1, 0)); }
+         res->density_l2_err = std::sqrt(sum);
+         if (opt->verbose && opt->rank == 0) { printf("Density L2 error: %g\n", res->density_l2_err); }
+      }
       if (opt->v_error && (opt->problem == 0 || opt->problem == 4))
       {
          // laghos.cpp:970-982: for problems 0 and 4 the exact velocity is constant in time

@@ -266,6 +266,7 @@ typedef struct lagb_run_options
    int gfprint;             // -print: <basename>_<ti>_{mesh,rho,v,e} (per-rank suffix .<rank:06d> when nranks > 1)
    int visit;               // -visit: <basename>_<ti:06d>.mfem_root + <basename>_<ti:06d>/<field>.<rank:06d>
    const char *basename;    // -k, default "results/Laghos" (the directory must exist)
+   int check_exact_sedov;   // -err: problem 1: L2 error of the density against the exact Sedov solution at t_final (laghos.cpp:1009-1085)
    int v_error;             // 1: problems 0 / 4: L_inf, L_1, L_2 velocity errors at the end of the run (laghos.cpp:970-982; host)
 } lagb_run_options;
 
@@ -287,6 +288,7 @@ typedef struct lagb_run_result
    double work_mdof;                // numerator of the FOM: 1e-6 * (H1 dofs x CG its + (H1+L2) dofs x stages + quad points x updates)
    double energy_init, energy_final; // IE + KE before / after the run (laghos.cpp:664-665, 956-962 "Energy diff")
    double v_err[3];                 // v_error: L_inf, L_1, L_2 of v - v0(x) (problems 0 and 4), else 0
+   double density_l2_err;           // check_exact_sedov: "Density L2 error", else 0
 } lagb_run_result;
 
 // hist: [2*hist_cap] (ti, |e|) pairs after every accepted step; S_out (optional): final state on the host

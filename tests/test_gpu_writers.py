@@ -52,3 +52,19 @@ def test_velocity_error_of_a_run(built):
     ro = pyoracle.run(**cfg, t_final=10.0, max_tsteps=5, want_state=True)             # CPU oracle: same end state
     assert np.allclose(r["v_err"], Problem(**cfg).velocity_error(ro["S"]), rtol=1e-7)
     assert run(**dict(cfg, problem=1), t_final=10.0, max_tsteps=2, v_error=True)["v_err"] == [0.0, 0.0, 0.0]
+
+
+def test_sedov_density_error_of_a_run(built):
+    """-err (laghos.cpp:1009-1085): "Density L2 error" of the driver = the host formula on the end state, with the
+    density projected by the CPU oracle's ComputeDensity; and the guard against shock reflections"""
+    import pyoracle
+    from laghos_b200.api import Problem, run
+    cfg = dict(mesh="cube01_hex", rs=1, problem=1, ok=2, ot=1)
+    r = run(**cfg, t_final=0.05, check_exact_sedov=True, want_state=True)
+    assert abs(r["t"] - 0.05) < 1e-14 and r["density_l2_err"] > 0
+    P = Problem(**cfg)
+    rho = pyoracle.Oracle(**cfg).compute_density(r["S"][:P.dim * P.ndofs_h1])
+    assert abs(r["density_l2_err"] - P.sedov_density_error(r["S"], rho, r["t"])) < 1e-8 * r["density_l2_err"]
+    # a coarse mesh smears the shock: the error is O(1) times sqrt(shock volume), far below the ambient norm 1
+    assert 0.01 < r["density_l2_err"] < 1.0
+    assert run(**cfg, t_final=0.01)["density_l2_err"] == 0.0

@@ -1,0 +1,124 @@
+"""`-err` of the reference driver (laghos.cpp:1009-1085): exact Sedov solution + L2 error of the density.
+
+The product's solution (host/sedov_exact.hpp) is its own restatement of the published similarity solution; the
+reference's (sedov/sedov_sol.cpp) is compiled from its sources into oracle/_ref (make ref) where /root/reference
+exists, and its outputs are committed as tests/golden/sedov_exact.json (tools/make_sedov_golden.py).
+
+Two separate statements are checked, because the reference's adaptive Gauss-Kronrod quadrature of the energy
+integral alpha stops short at the integrable end-point singularity (it differs from the published values of
+Kamm & Timmes, LA-UR-07-2849, Table 1 -- 0.538743 / 0.984074 / 0.851072 for gamma = 1.4 -- in the 5th digit):
+  * with the reference's alpha, the similarity profiles agree: p to 1e-12, r2 / U / post-shock state to 1e-14, rho and v
+    to 1e-6 (the reference's bisection for V(r) stops at ~1e-8);
+  * the product's own alpha reproduces the published values to all six printed digits and is within 5e-5 of the reference's.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from laghos_b200.api import LagbError, Problem, sedov_exact
+from test_error_norms import lagrange
+from test_tables_independent import gauss01, gll01
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "sedov_exact.json")))["cases"]
+rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-300)))
+
+
+@pytest.mark.parametrize("k", range(len(GOLD)))
+def test_profiles_against_reference_vectors(built, k):
+    c = GOLD[k]
+    r = np.array(c["r"])
+    kw = dict(gamma=c["gamma"], rho0=c["rho0"], blast_energy=c["blast_energy"])
+    rho, v, p, info = sedov_exact(c["dim"], c["t"], r, alpha=c["info"]["alpha"], **kw)
+    ref = c["info"]
+    assert rel(info, [ref[n] for n in ("alpha", "r2", "U", "rho2", "v2", "p2")]) < 1e-14
+    assert rel(p, c["p"]) < 1e-12 and rel(rho, c["rho"]) < 1e-6 and rel(v, c["v"]) < 1e-6
+    assert np.all(rho[-3:] == c["rho0"]) and np.all(v[-3:] == 0) and np.all(p[-3:] == 0)      # ahead of the shock
+    # own energy integral: the reference's quadrature error bounds the difference
+    own = sedov_exact(c["dim"], c["t"], r, **kw)
+    assert abs(own[3][0] - ref["alpha"]) < 5e-5 * ref["alpha"]
+    assert rel(own[0], c["rho"]) < 3e-4 and rel(own[2], c["p"]) < 1e-4
+
+
+def test_energy_integral_published_values(built):
+    # Kamm & Timmes, Table 1 (gamma = 1.4, uniform density): planar, cylindrical, spherical
+    for dim, alpha in ((1, 0.538743), (2, 0.984074), (3, 0.851072)):
+        assert abs(sedov_exact(dim, 1.0, np.array([0.1]))[3][0] - alpha) < 5e-7
+    # self-consistency: the energy of the evaluated profiles is the blast energy (spherical shells, fine radial rule)
+    for dim in (2, 3):
+        E0, t = 0.7, 0.4
+        info = sedov_exact(dim, t, np.array([0.1]), blast_energy=E0)[3]
+        x, w = np.polynomial.legendre.leggauss(200)
+        edges = info[1] * (1 - np.geomspace(1, 1e-9, 60))        # panels clustered at the shock
+        tot = 0.0
+        for a, b in zip(edges[:-1], edges[1:]):
+            r = 0.5 * (a + b) + 0.5 * (b - a) * x
+            rho, v, p, _ = sedov_exact(dim, t, r, blast_energy=E0)
+            shell = 2 * np.pi * r if dim == 2 else 4 * np.pi * r * r
+            tot += 0.5 * (b - a) * np.sum(w * shell * (0.5 * rho * v * v + p / 0.4))
+        assert abs(tot - E0) < 2e-6 * E0
+    with pytest.raises(LagbError):
+        sedov_exact(3, 0.0, np.array([0.1]))
+    with pytest.raises(LagbError):
+        sedov_exact(4, 1.0, np.array([0.1]))
+
+
+def test_against_compiled_reference(built):
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libsedov_ref.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref not built (no /root/reference here): covered by the committed vectors")
+    lib = C.CDLL(lib_path)
+    dp = C.POINTER(C.c_double)
+    lib.sedov_ref_eval.argtypes = [C.c_int] + [C.c_double] * 5 + [C.c_int] + [dp] * 5
+    rng = np.random.default_rng(5)
+    for dim in (2, 3):
+        t, E0 = 0.37, 1.0
+        info = np.zeros(6)
+        r = np.sort(rng.uniform(0.15, 1.3, 64))
+        rho, v, p = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+        q = lambda a: a.ctypes.data_as(dp)
+        assert lib.sedov_ref_eval(dim, 1.4, 1.0, E0, 0.0, t, r.size, q(r), q(rho), q(v), q(p), q(info)) == 0
+        mine = sedov_exact(dim, t, r, alpha=info[0])
+        assert rel(mine[2], p) < 1e-12 and rel(mine[0], rho) < 1e-6 and rel(mine[1], v) < 1e-6
+
+
+@pytest.mark.parametrize("mesh,rs,ok,ot", [("cube01_hex", 1, 2, 1), ("square01_quad", 2, 3, 2)])
+def test_density_error_against_numpy(built, mesh, rs, ok, ot):
+    P = Problem(mesh=mesh, rs=rs, problem=1, ok=ok, ot=ot)
+    dim, D, L1, NE = P.dim, P.D1D, P.L1D, P.NE
+    rng = np.random.default_rng(2)
+    S = np.array(P.S0)
+    nv = dim * P.ndofs_h1
+    S[:nv] += 0.02 / (2 ** rs * 2 * ok) * rng.standard_normal(nv)
+    rho = 1.0 + 0.5 * rng.random(P.ndofs_l2)
+    t = 0.3
+    got = P.sedov_density_error(S, rho, t)
+    # numpy restatement: err_order = 2 max(2 (max(ok, ot) + 1), oq = -1) -> err_order / 2 + 1 points per axis
+    n = 2 * (max(ok, ot) + 1) + 1
+    gx, gw = gauss01(n)
+    B, G = lagrange(gll01(D), gx)
+    from math import comb
+    BL = np.array([[comb(ot, l) * x ** l * (1 - x) ** (ot - l) for l in range(L1)] for x in gx])
+    X = S[:nv].reshape(dim, -1)[:, P.h1_map].reshape((dim, NE) + (D,) * dim)
+    R = rho.reshape((NE,) + (L1,) * dim)
+    if dim == 2:
+        ev = lambda T, Ay, Ax: np.einsum("ceyx,qy,px->ceqp", T, Ay, Ax)
+        xq = ev(X, B, B)
+        J = np.stack([ev(X, B, G), ev(X, G, B)], axis=1)
+        det = J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0]
+        rq = np.einsum("eyx,qy,px->eqp", R, BL, BL)
+        w = np.einsum("q,p->qp", gw, gw)
+    else:
+        ev = lambda T, Az, Ay, Ax: np.einsum("cezyx,rz,qy,px->cerqp", T, Az, Ay, Ax)
+        xq = ev(X, B, B, B)
+        J = np.stack([ev(X, B, B, G), ev(X, B, G, B), ev(X, G, B, B)], axis=1)
+        det = np.linalg.det(np.moveaxis(J, (0, 1), (-2, -1)))
+        rq = np.einsum("ezyx,rz,qy,px->erqp", R, BL, BL, BL)
+        w = np.einsum("r,q,p->rqp", gw, gw, gw)
+    radius = np.sqrt((xq ** 2).sum(axis=0))
+    rex = sedov_exact(dim, t, radius.ravel())[0].reshape(radius.shape)
+    ref = np.sqrt((w * det * (rex - rq) ** 2).sum())
+    assert abs(got - ref) < 1e-12 * ref, (got, ref)
