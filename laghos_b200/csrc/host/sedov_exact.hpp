@@ -7,8 +7,8 @@
 //   * the two energy integrals (integrable end-point singularity s^(-0.68) in 3D) use tanh-sinh quadrature, whose
 //     nodes cluster double-exponentially at the end points and are generated directly as distances from them;
 //   * V(r) comes from a bracketed Newton iteration on log lambda.
-// Checked against the reference's own compiled solution (oracle/_ref/libsedov_ref.so, built from
-// /root/reference/sedov where that tree exists) through the committed vectors tests/golden/sedov_exact.json.
+// Checked in tests/test_sedov_exact.py against the reference's own solution compiled from its sources (test
+// infrastructure, only where the reference tree exists) through the committed vectors tests/golden/sedov_exact.json.
 // Host code, diagnostics only (row 8f-2).  Only the "standard" case V2 < Vs is implemented (true for every
 // gamma > 1 with omega = 0 in 2D and 3D ... checked in the constructor); the singular / vacuum cases need omega > 0.
 #pragma once
