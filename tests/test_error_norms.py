@@ -105,3 +105,36 @@ def test_closed_form_and_convergence(built):
     S = np.array(R.S0)
     S[3 * R.ndofs_h1:4 * R.ndofs_h1] = 2.0                 # v_y = 2 everywhere on the unit cube
     assert np.allclose(R.velocity_error(S), (2.0, 2.0, 2.0), rtol=1e-13)
+
+
+@pytest.mark.parametrize("pgrid", [(2, 1, 1), (2, 2, 1), (2, 2, 2)])
+def test_rank_blocks_add_up(built, pgrid):
+    """partitioned runs reduce the per-rank values (max / sum / sum of squares): the blocks of the initial state must
+    reproduce the one-rank norms -- velocity errors (problem 0) and the Sedov density error (problem 1)"""
+    import ctypes as C
+    nr = pgrid[0] * pgrid[1] * pgrid[2]
+    cfg = dict(mesh="cube01_hex", rs=1, ok=2, ot=1)
+    G = Problem(problem=0, **cfg)
+    S = np.array(G.S0)
+    S[3 * G.ndofs_h1:6 * G.ndofs_h1] *= 0.9                 # v = 0.9 v0: a non-trivial error field, the same on every rank
+    ref = G.velocity_error(S)
+    mx, l1, l2sq = 0.0, 0.0, 0.0
+    for rank in range(nr):
+        P = Problem(problem=0, rank=rank, pgrid=pgrid, **cfg)
+        Sl = np.array(P.S0)
+        Sl[3 * P.ndofs_h1:6 * P.ndofs_h1] *= 0.9
+        out = (C.c_double * 4)()
+        assert P.lib.lagb_problem_velocity_error(P.h, Sl.ctypes.data_as(C.c_void_p), out) == 0
+        mx, l1, l2sq = max(mx, out[0]), l1 + out[1], l2sq + out[3]
+    assert np.allclose((mx, l1, np.sqrt(l2sq)), ref, rtol=1e-12)
+    G = Problem(problem=1, **cfg)
+    ref = G.sedov_density_error(np.array(G.S0), np.array(G.rho0_gf), 0.2)
+    tot = 0.0
+    for rank in range(nr):
+        P = Problem(problem=1, rank=rank, pgrid=pgrid, **cfg)
+        out = (C.c_double * 2)()
+        S0, r0 = np.array(P.S0), np.array(P.rho0_gf)
+        assert P.lib.lagb_problem_sedov_density_error(P.h, S0.ctypes.data_as(C.c_void_p), r0.ctypes.data_as(C.c_void_p),
+                                                      0.2, 1.4, 1.0, 1.0, out) == 0
+        tot += out[1]
+    assert abs(np.sqrt(tot) - ref) < 1e-12 * ref and ref > 0.1
