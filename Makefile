@@ -25,10 +25,10 @@ build/laghos_shim.o: laghos_b200/shim/laghos_shim.cpp laghos_b200/shim/laghos_sh
 laghos_b200/lib/liblaghos_b200.so: $(OBJ)
 	@mkdir -p laghos_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -ldl
-oracle/_build/liboracle.so: oracle/oracle_capi.cpp oracle/laghos_oracle.hpp oracle/smallmat.hpp $(HOST_HDRS)
+oracle/_build/liboracle.so: oracle/oracle_capi.cpp oracle/laghos_oracle.hpp oracle/own_tables.hpp oracle/smallmat.hpp $(HOST_HDRS)
 	@mkdir -p oracle/_build
 	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -o $@ oracle/oracle_capi.cpp -lpthread
-oracle/_build/oracle_cli: oracle/oracle_main.cpp oracle/laghos_oracle.hpp oracle/smallmat.hpp $(HOST_HDRS)
+oracle/_build/oracle_cli: oracle/oracle_main.cpp oracle/laghos_oracle.hpp oracle/own_tables.hpp oracle/smallmat.hpp $(HOST_HDRS)
 	@mkdir -p oracle/_build
 	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -o $@ oracle/oracle_main.cpp -lpthread
 

@@ -13,11 +13,13 @@
 //   * hydro operator + RK4/RK2Avg  : laghos_solver.cpp:308-540, 1436-1487; MFEM RK4Solver
 //   * time loop with dt control    : laghos.cpp:706-778, 792-795
 // One element at a time, stack arrays, sum factorisation — the same algorithm the
-// reference runs on a CPU.  Setup (mesh, tables, ICs) comes from
-// laghos_b200/csrc/host/problem.hpp.
+// reference runs on a CPU.  Mesh and initial conditions come from
+// laghos_b200/csrc/host/problem.hpp; the 1D tables, quadrature weights and the gather map are the oracle's own
+// (own_tables.hpp: independent algorithms, cross-checked against the host set-up, then used instead of it).
 #pragma once
 #include "../laghos_b200/csrc/host/problem.hpp"
 #include "smallmat.hpp"
+#include "own_tables.hpp"
 #include <chrono>
 #include <cstring>
 #include <limits>

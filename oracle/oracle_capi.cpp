@@ -25,7 +25,7 @@ void *orc_create(const char *mesh, int rs, int problem, int ok, int ot, int oq, 
       sp.problem = problem; sp.dim = dim; sp.ok = ok; sp.ot = ot; sp.oq = oq;
       sp.blast_scale = blast_scale; sp.impose_visc = impose_visc != 0;
       OrcHandle *h = new OrcHandle();
-      h->P.build(sp, rm);
+      h->P.build(sp, rm); oracle::install_own_tables(h->P);
       h->H = new oracle::Hydro(h->P, cfl, cgt, cgm, nthreads);
       return h;
    }
@@ -45,7 +45,7 @@ void *orc_create_part(const char *mesh, int rs, int problem, int ok, int ot, int
       sp.blast_scale = blast_scale; sp.impose_visc = impose_visc != 0;
       lagb::Partition part; part.build(dim, rm.n, pgrid, rank, ok);
       OrcHandle *h = new OrcHandle();
-      h->P.build(sp, rm, part.lo, part.hi);
+      h->P.build(sp, rm, part.lo, part.hi); oracle::install_own_tables(h->P);
       h->H = new oracle::Hydro(h->P, cfl, cgt, cgm, nthreads);
       return h;
    }
@@ -141,7 +141,7 @@ int orc_run(const char *mesh, int rs, int problem, int ok, int ot, int oq, doubl
       lagb::ProblemSpec sp;
       sp.problem = problem; sp.dim = dim; sp.ok = ok; sp.ot = ot; sp.oq = oq;
       sp.blast_scale = blast_scale; sp.impose_visc = impose_visc != 0;
-      lagb::Problem P; P.build(sp, rm);
+      lagb::Problem P; P.build(sp, rm); oracle::install_own_tables(P);
       oracle::RunOptions o;
       o.ode_solver_type = ode_solver_type; o.t_final = t_final; o.max_tsteps = max_tsteps;
       o.cfl = cfl; o.cg_tol = cgt; o.cg_max_iter = cgm; o.nthreads = nthreads; o.verbose = false;

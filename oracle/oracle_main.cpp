@@ -54,7 +54,7 @@ int main(int argc, char **argv)
    sp.dim = dim;
    sp.blast_scale = serial ? 0.25 : E0/pow(2, dim);
    lagb::RectMesh rm; rm.build(dim, coarse, rs);
-   lagb::Problem P; P.build(sp, rm);
+   lagb::Problem P; P.build(sp, rm); oracle::install_own_tables(P);
    printf("Zones: %d, H1 vdofs: %lld, L2 dofs: %lld, Q1D %d\n", P.NE, (long long)P.h1_vsize(), (long long)P.ndofs_l2, P.Q1D);
    oracle::RunResult r = oracle::run(P, opt);
    printf("final: steps %d ti %d t %.6f dt %.6f |e| %.15e\n", r.steps, r.ti_last, r.t, r.dt, r.e_norm);
