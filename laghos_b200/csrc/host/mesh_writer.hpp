@@ -13,6 +13,7 @@
 // Ordering 0 (byNODES): all values of component 0, then component 1, ...
 #pragma once
 #include "problem.hpp"
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <iomanip>
@@ -120,27 +121,34 @@ inline void write_l2_field(std::ostream &os, const Problem &P, const double *h_f
    for (int64_t i = 0; i < P.ndofs_l2; i++) { os << h_f[i] << "\n"; }
 }
 
-// <collection>_<cycle>.mfem_root of VisItDataCollection::Save (JSON; the per-rank files live in
-// <collection>_<cycle>/<field>.<rank> with 6-digit cycle and rank).  fields: (name, components).
+// <collection>_<cycle>.mfem_root of VisItDataCollection::Save (JSON).  As in MFEM's DataCollection the collection name
+// may carry a directory prefix ("results/Laghos"): the root file and the per-cycle directory live under the prefix, and
+// the paths INSIDE the root file are relative to it ("Laghos_000005/mesh.%06d", 6-digit cycle and rank).  Every field
+// is tagged assoc "nodes" with lod = its polynomial order (>= 1); mesh format "0" = serial-format files, one per rank.
+// fields: (name, components, order).
+struct VisitField { std::string name; int comps, order; };
 inline void write_visit_root(std::ostream &os, const std::string &collection, int cycle, double time, double time_step,
-                             int nranks, int dim, const std::vector<std::pair<std::string,int>> &fields)
+                             int nranks, int dim, const std::vector<VisitField> &fields)
 {
    char cyc[32]; snprintf(cyc, sizeof(cyc), "%06d", cycle);
-   const std::string dir = collection + "_" + cyc + "/";
+   const size_t slash = collection.find_last_of('/');
+   const std::string name = (slash == std::string::npos) ? collection : collection.substr(slash + 1);
+   const std::string dir = name + "_" + cyc + "/";
    os << "{\n  \"dsets\": {\n    \"main\": {\n"
       << "      \"cycle\": " << cycle << ",\n"
       << "      \"domains\": " << nranks << ",\n"
       << "      \"fields\": {\n";
    for (size_t i = 0; i < fields.size(); i++)
    {
-      os << "        \"" << fields[i].first << "\": {\n"
-         << "          \"path\": \"" << dir << fields[i].first << ".%06d\",\n"
-         << "          \"tags\": { \"assoc\": \"nodes\", \"comps\": \"" << fields[i].second << "\", \"lod\": \"1\" }\n"
+      os << "        \"" << fields[i].name << "\": {\n"
+         << "          \"path\": \"" << dir << fields[i].name << ".%06d\",\n"
+         << "          \"tags\": { \"assoc\": \"nodes\", \"comps\": \"" << fields[i].comps << "\", \"lod\": \""
+         << std::max(1, fields[i].order) << "\" }\n"
          << "        }" << (i + 1 < fields.size() ? "," : "") << "\n";
    }
    os << "      },\n"
       << "      \"mesh\": {\n"
-      << "        \"format\": \"1\",\n"
+      << "        \"format\": \"0\",\n"
       << "        \"path\": \"" << dir << "mesh.%06d\",\n"
       << "        \"tags\": { \"max_lods\": \"32\", \"spatial_dim\": \"" << dim << "\", \"topo_dim\": \"" << dim << "\" }\n"
       << "      },\n"
@@ -188,21 +196,21 @@ inline bool write_visit_files(const Problem &P, const std::string &collection, i
       if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) { err = "cannot create directory " + dir; return false; }
    }
    const int64_t NV = P.h1_vsize();
-   std::vector<std::pair<std::string,int>> fields;
+   std::vector<VisitField> fields;
    bool ok = write_text_file(dir + "/mesh." + rk, err, [&](std::ostream &os) { write_mfem_mesh(os, P, S, precision); });
    if (ok && rho)
    {
-      fields.push_back({"Density", 1});
+      fields.push_back({"Density", 1, P.spec.ot});
       ok = write_text_file(dir + "/Density." + rk, err, [&](std::ostream &os) { write_l2_field(os, P, rho, precision); });
    }
    if (ok)
    {
-      fields.push_back({"Velocity", P.dim});
+      fields.push_back({"Velocity", P.dim, P.spec.ok});
       ok = write_text_file(dir + "/Velocity." + rk, err, [&](std::ostream &os) { write_h1_field(os, P, S + NV, P.dim, precision); });
    }
    if (ok)
    {
-      fields.push_back({"Specific Internal Energy", 1});
+      fields.push_back({"Specific Internal Energy", 1, P.spec.ot});
       ok = write_text_file(dir + "/Specific Internal Energy." + rk, err, [&](std::ostream &os) { write_l2_field(os, P, S + 2*NV, precision); });
    }
    if (ok && rank == 0)

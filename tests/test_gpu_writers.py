@@ -35,9 +35,10 @@ def test_print_and_visit_files_of_a_run(built, tmp_path):
     assert abs(rho.mean() - 1.0) < 0.2
     root = json.load(open(f"{base}_{last:06d}.mfem_root"))["dsets"]["main"]
     assert root["cycle"] == last and root["domains"] == 1 and abs(root["time"] - r["t"]) < 1e-12
+    here = os.path.dirname(base)                      # paths in the root file are relative to its directory
     for f in list(root["fields"].values()) + [root["mesh"]]:
-        assert os.path.isfile(f["path"] % 0)
-    _, _, _, e2 = parse_gf(root["fields"]["Specific Internal Energy"]["path"] % 0)
+        assert os.path.isfile(os.path.join(here, f["path"] % 0))
+    _, _, _, e2 = parse_gf(os.path.join(here, root["fields"]["Specific Internal Energy"]["path"] % 0))
     assert np.array_equal(e2, e)
 
 

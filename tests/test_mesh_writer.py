@@ -157,16 +157,21 @@ def test_print_files(built, tmp_path):
 def test_visit_collection(built, tmp_path):
     P = Problem(mesh="square01_quad", rs=1, problem=0, ok=2, ot=1)
     S = np.array(P.S0)
-    coll = str(tmp_path / "Laghos")
+    os.makedirs(tmp_path / "results")
+    coll = str(tmp_path / "results" / "Laghos")             # the reference's default basename "results/Laghos"
     P.write_visit(coll, 7, 0.25, 0.01, S, rho=np.ones(P.ndofs_l2))
     root = json.load(open(coll + "_000007.mfem_root"))["dsets"]["main"]
     assert root["cycle"] == 7 and root["domains"] == 1 and root["time"] == 0.25 and root["time_step"] == 0.01
-    assert root["mesh"]["tags"]["spatial_dim"] == "2"
+    assert root["mesh"]["tags"]["spatial_dim"] == "2" and root["mesh"]["format"] == "0"
     assert set(root["fields"]) == {"Density", "Velocity", "Specific Internal Energy"}   # laghos.cpp:695-697
-    assert os.path.isfile(root["mesh"]["path"] % 0)
+    # paths are relative to the root file's directory (MFEM DataCollection: prefix path + name)
+    assert root["mesh"]["path"] == "Laghos_000007/mesh.%06d"
+    here = os.path.dirname(coll)
+    assert os.path.isfile(os.path.join(here, root["mesh"]["path"] % 0))
     for name, f in root["fields"].items():
-        fec, vdim, _, vals = parse_gf(f["path"] % 0)
-        assert int(f["tags"]["comps"]) == vdim
+        fec, vdim, _, vals = parse_gf(os.path.join(here, f["path"] % 0))
+        assert int(f["tags"]["comps"]) == vdim and f["tags"]["assoc"] == "nodes"
+        assert f["tags"]["lod"] == ("2" if name == "Velocity" else "1")
         assert fec.startswith("L2_T1_2D_P2" if name == "Velocity" else "L2_T2_2D_P1")
     # a second cycle into a new directory, without a density field; rank 1 of 2 writes no root file
     P.write_visit(coll, 8, 0.3, 0.01, S, rank=1, nranks=2)
