@@ -11,10 +11,27 @@
 #pragma once
 #include "problem.hpp"
 #include "sedov_exact.hpp"
+#include <algorithm>
 #include <cmath>
+#include <thread>
 #include <vector>
 
 namespace lagb {
+
+// element ranges over the host threads (diagnostics at benchmark size: 262 144 elements x 9^3 points); the partial
+// results are combined in chunk order, so the value is reproducible for a given thread count
+template <class F> inline void for_element_chunks(int NE, int &nchunks, F &&body)
+{
+   const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+   nchunks = std::max(1, std::min(std::min(hw, 256), NE/64));
+   std::vector<std::thread> pool;
+   for (int k = 0; k < nchunks; k++)
+   {
+      const int e0 = (int)((long long)NE*k/nchunks), e1 = (int)((long long)NE*(k + 1)/nchunks);
+      if (nchunks == 1) { body(k, e0, e1); } else { pool.emplace_back([&body, k, e0, e1]() { body(k, e0, e1); }); }
+   }
+   for (auto &t : pool) { t.join(); }
+}
 
 // out[0] = max, out[1] = L1 sum, out[2] = L2 sum of SQUARES (take the root after the rank reduction)
 inline void velocity_error_sums(const Problem &P, const double *S, double out[3])
@@ -28,8 +45,12 @@ inline void velocity_error_sums(const Problem &P, const double *S, double out[3]
    const double *X = S, *V = S + P.h1_vsize();
    ICs ic {P.spec.problem, dim};
    const int nz = (dim == 3) ? n : 1, DZ = (dim == 3) ? D : 1;
+   std::vector<double> part(3*256, 0.0);
+   int nchunks = 1;
+   for_element_chunks(P.NE, nchunks, [&](int chunk, int e_begin, int e_end)
+   {
    double emax = 0.0, e1 = 0.0, e2 = 0.0;
-   for (int e = 0; e < P.NE; e++)
+   for (int e = e_begin; e < e_end; e++)
    {
       const int *map = &P.h1_map[(size_t)e*P.ND];
       for (int qz = 0; qz < nz; qz++)
@@ -67,7 +88,10 @@ inline void velocity_error_sums(const Problem &P, const double *S, double out[3]
                emax = std::max(emax, err); e1 += w*err; e2 += w*err*err;
             }
    }
-   out[0] = emax; out[1] = e1; out[2] = e2;
+   part[3*chunk] = emax; part[3*chunk + 1] = e1; part[3*chunk + 2] = e2;
+   });
+   out[0] = out[1] = out[2] = 0.0;
+   for (int k = 0; k < nchunks; k++) { out[0] = std::max(out[0], part[3*k]); out[1] += part[3*k + 1]; out[2] += part[3*k + 2]; }
 }
 
 // `-err` of the reference driver (laghos.cpp:1009-1085): L2 error of the density against the exact Sedov solution at
@@ -90,8 +114,12 @@ inline double sedov_density_error_sum(const Problem &P, const double *S, const d
    }
    const int64_t nd = P.ndofs_h1;
    const int nz = (dim == 3) ? n : 1, DZ = (dim == 3) ? D : 1, LZ = (dim == 3) ? L1 : 1;
+   std::vector<double> part(256, 0.0);
+   int nchunks = 1;
+   for_element_chunks(P.NE, nchunks, [&](int chunk, int e_begin, int e_end)
+   {
    double sum = 0.0;
-   for (int e = 0; e < P.NE; e++)
+   for (int e = e_begin; e < e_end; e++)
    {
       const int *map = &P.h1_map[(size_t)e*P.ND];
       const double *re = rho + (size_t)e*P.NL;
@@ -135,7 +163,11 @@ inline double sedov_density_error_sum(const Problem &P, const double *S, const d
                sum += w*(rex - rh)*(rex - rh);
             }
    }
-   return sum;
+   part[chunk] = sum;
+   });
+   double total = 0.0;
+   for (int k = 0; k < nchunks; k++) { total += part[k]; }
+   return total;
 }
 
 } // namespace lagb

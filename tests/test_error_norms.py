@@ -71,7 +71,8 @@ def numpy_errors(P, S, problem):
 
 
 @pytest.mark.parametrize("mesh,rs,problem,ok", [("square01_quad", 2, 0, 2), ("square01_quad", 1, 0, 4),
-                                                ("cube01_hex", 1, 0, 3), ("square_gresho", 1, 4, 3)])
+                                                ("cube01_hex", 1, 0, 3), ("square_gresho", 1, 4, 3),
+                                                ("cube01_hex", 2, 0, 2)])      # 512 elements: the threaded element loop
 def test_against_numpy(built, mesh, rs, problem, ok):
     P = Problem(mesh=mesh, rs=rs, problem=problem, ok=ok, ot=ok - 1)
     rng = np.random.default_rng(11)

@@ -85,7 +85,8 @@ def test_against_compiled_reference(built):
         assert rel(mine[2], p) < 1e-12 and rel(mine[0], rho) < 1e-6 and rel(mine[1], v) < 1e-6
 
 
-@pytest.mark.parametrize("mesh,rs,ok,ot", [("cube01_hex", 1, 2, 1), ("square01_quad", 2, 3, 2)])
+@pytest.mark.parametrize("mesh,rs,ok,ot", [("cube01_hex", 1, 2, 1), ("square01_quad", 2, 3, 2),
+                                           ("cube01_hex", 2, 2, 1)])           # 512 elements: the threaded element loop
 def test_density_error_against_numpy(built, mesh, rs, ok, ot):
     P = Problem(mesh=mesh, rs=rs, problem=1, ok=ok, ot=ot)
     dim, D, L1, NE = P.dim, P.D1D, P.L1D, P.NE
