@@ -98,6 +98,16 @@ const double *lagb_problem_qweights(const lagb_problem *p);       /* [NQ] */
 /* 1D tables: which = 0:B 1:G (H1, [q + Q1D*d]), 2:BL (L2 Bernstein, [q + Q1D*l]), 3:qx 4:qw */
 const double *lagb_problem_table(const lagb_problem *p, int which);
 
+/* The reference driver's self-test `--checks` (laghos.cpp:904-926, 1403-1474; table it_norms :1441-1463).
+ *   lagb_checks_entry : entry k (0, 1) of the table for (dim, problem): step index and |e|
+ *   lagb_checks_step  : the reference's Checks(ti, |e|, chk): *chk is incremented when the table has an entry at this
+ *                       step; returns LAGB_OK (no entry, or the entry matched) or LAGB_ERR_INVALID on a mismatch
+ *                       (lagb_last_error() = "P<problem>, #<step>"); eps is the reference's 1e-13, both relative
+ *                       errors must be below it
+ * The run option `check` of lagb_laghos_run applies it after every accepted step and requires two hits at the end. */
+int lagb_checks_entry(int dim, int problem, int k, int32_t *it, double *norm);
+int lagb_checks_step(int dim, int problem, int ti, double e_norm, double eps, int32_t *chk);
+
 /* End-of-run velocity error norms of the reference driver for problems 0 and 4 (laghos.cpp:970-982:
  * ComputeMaxError / ComputeL1Error / ComputeL2Error against the initial velocity field, which is the exact solution
  * there), from the HOST copy of the state S = (x | v | e): Gauss-Legendre rule of order 2 ok + 3 per element, exact

@@ -43,7 +43,8 @@ class RunOptions(C.Structure):
                 ("warmup_steps", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("pgrid", C.c_int * 3),
                 ("nccl_id", C.c_void_p), ("profile_mass", C.c_int),
                 ("gfprint", C.c_int), ("visit", C.c_int), ("basename", C.c_char_p),
-                ("check_exact_sedov", C.c_int), ("v_error", C.c_int)]
+                ("check_exact_sedov", C.c_int), ("v_error", C.c_int),
+                ("check", C.c_int), ("check_eps", C.c_double)]
 
 
 class RunResult(C.Structure):
@@ -57,7 +58,7 @@ class RunResult(C.Structure):
                 ("mass_kernel_seconds", C.c_double), ("mass_kernel_launches", C.c_int64),
                 ("mass_kernel_ncomp", C.c_int64), ("work_mdof", C.c_double),
                 ("energy_init", C.c_double), ("energy_final", C.c_double),
-                ("v_err", C.c_double * 3), ("density_l2_err", C.c_double)]
+                ("v_err", C.c_double * 3), ("density_l2_err", C.c_double), ("checks", C.c_int)]
 
 
 # every symbol include/laghos_b200.h declares (tests/test_abi_symbols.py checks the
@@ -76,7 +77,7 @@ lagb_vec_copy lagb_vec_axpby lagb_vec_dot lagb_nccl_unique_id lagb_ctx_comm_init
 lagb_timing_get lagb_timing_reset lagb_stopwatch_start lagb_stopwatch_stop
 lagb_profile_mass lagb_profile_mass_get lagb_vmass_mult_all lagb_tune_set lagb_internal_energy lagb_kinetic_energy
 lagb_host_batch_plan_check lagb_compute_density lagb_pcg_vmass_all_x0
-lagb_problem_velocity_error lagb_sedov_exact_eval lagb_problem_sedov_density_error lagb_problem_write_mesh lagb_problem_write_field lagb_problem_write_print lagb_problem_write_visit""".split()
+lagb_checks_entry lagb_checks_step lagb_problem_velocity_error lagb_sedov_exact_eval lagb_problem_sedov_density_error lagb_problem_write_mesh lagb_problem_write_field lagb_problem_write_print lagb_problem_write_visit""".split()
 
 
 def load_library():
@@ -115,6 +116,8 @@ def load_library():
     lib.lagb_problem_table.argtypes = [vp, i32]
     lib.lagb_problem_table.restype = c_double_p
     lib.lagb_problem_velocity_error.argtypes = [vp, vp, c_double_p]
+    lib.lagb_checks_entry.argtypes = [i32, i32, i32, c_int_p, c_double_p]
+    lib.lagb_checks_step.argtypes = [i32, i32, i32, dbl, dbl, c_int_p]
     lib.lagb_sedov_exact_eval.argtypes = [i32, dbl, dbl, dbl, dbl, dbl, i32, vp, vp, vp, vp, vp]
     lib.lagb_problem_sedov_density_error.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl, c_double_p]
     lib.lagb_problem_write_mesh.argtypes = [vp, vp, C.c_char_p, i32]

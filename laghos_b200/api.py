@@ -375,7 +375,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
         ode_solver_type=4, t_final=0.6, max_tsteps=-1, cfl=0.5, cg_tol=1e-8, cg_max_iter=300,
         batched_pcg=True, kernel_variant=0, device=0, verbose=False, vis_steps=5, e2e_host_state=False,
         warmup_steps=0, rank=0, nranks=1, pgrid=(1, 1, 1), nccl_id=None, hist_cap=0, want_state=False,
-        profile_mass=False, gfprint=False, visit=False, basename=None, v_error=False, check_exact_sedov=False):
+        profile_mass=False, gfprint=False, visit=False, basename=None, v_error=False, check_exact_sedov=False, check=False, check_eps=0.0):
     """The reference driver's run (laghos.cpp main) through the C++ shim: lagb_laghos_run."""
     lib = load_library()
     dim = mesh_dim(mesh)
@@ -395,6 +395,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
     o.profile_mass = int(profile_mass)
     o.gfprint, o.visit, o.v_error = int(gfprint), int(visit), int(v_error)
     o.check_exact_sedov = int(check_exact_sedov)
+    o.check, o.check_eps = int(check), check_eps
     base_b = None if basename is None else str(basename).encode()   # kept alive until the call returns
     if base_b is not None:
         o.basename = base_b
@@ -421,7 +422,7 @@ def run(mesh="cube01_hex", rs=2, problem=1, ok=2, ot=1, oq=-1, blast_scale=None,
                quad_tstep=r.timing.quad_tstep, wall_seconds=r.wall_seconds, device_seconds=r.device_seconds,
                mass_kernel_seconds=r.mass_kernel_seconds, mass_kernel_launches=r.mass_kernel_launches,
                mass_kernel_ncomp=r.mass_kernel_ncomp, work_mdof=r.work_mdof,
-               energy_init=r.energy_init, energy_final=r.energy_final, v_err=list(r.v_err), density_l2_err=r.density_l2_err,
+               energy_init=r.energy_init, energy_final=r.energy_final, v_err=list(r.v_err), density_l2_err=r.density_l2_err, checks=r.checks,
                h2d_bytes_per_step=r.h2d_bytes_per_step, d2h_bytes_per_step=r.d2h_bytes_per_step,
                kernel_launches=r.kernel_launches, ndofs_h1_global=r.ndofs_h1_global,
                ndofs_l2_global=r.ndofs_l2_global, ne_global=r.ne_global,

@@ -5,6 +5,7 @@
 #include "host/mesh_reader.hpp"
 #include "host/mesh_writer.hpp"
 #include "host/error_norms.hpp"
+#include "host/checks.hpp"
 #include <string>
 
 namespace lagb { void set_error(const std::string &msg); }
@@ -129,6 +130,25 @@ const double *lagb_problem_table(const lagb_problem *p, int which)
       case 3: return p->P.tab.qx.data(); case 4: return p->P.tab.qw.data();
    }
    return nullptr;
+}
+
+int lagb_checks_entry(int dim, int problem, int k, int32_t *it, double *norm)
+{
+   if (dim < 2 || dim > 3 || problem < 0 || problem > 7 || k < 0 || k > 1 || !it || !norm)
+   { lagb::set_error("checks_entry: bad argument"); return LAGB_ERR_INVALID; }
+   const lagb::CheckEntry &c = lagb::checks_table[(dim - 2)*8 + problem][k];
+   *it = c.it; *norm = c.norm;
+   return LAGB_OK;
+}
+
+int lagb_checks_step(int dim, int problem, int ti, double e_norm, double eps, int32_t *chk)
+{
+   if (!chk) { lagb::set_error("checks_step: null argument"); return LAGB_ERR_INVALID; }
+   std::string msg; int n = *chk;
+   const int rc = lagb::checks_step(dim, problem, ti, e_norm, eps, n, msg);
+   *chk = n;
+   if (rc < 0) { lagb::set_error(msg); return LAGB_ERR_INVALID; }
+   return LAGB_OK;
 }
 
 int lagb_problem_velocity_error(const lagb_problem *p, const double *h_S, double out[4])

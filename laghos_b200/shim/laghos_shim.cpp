@@ -5,7 +5,11 @@
 #include "../csrc/host/partition.hpp"
 #include "../csrc/host/mesh_writer.hpp"
 #include "../csrc/host/error_norms.hpp"
+#include "../csrc/host/checks.hpp"
 #include <chrono>
+#include <string>
+
+namespace lagb { void set_error(const std::string &msg); }
 #include <cmath>
 #include <cstring>
 
@@ -426,7 +430,13 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
          t_wall0 = std::chrono::steady_clock::now();
          LAGHOS_CHECK(lagb_stopwatch_start(ctx)); sw_started = true;
       }
-      int n_hist = 0, ti = 1;
+      int n_hist = 0, ti = 1, checks = 0;
+      if (opt->check)
+      {
+         const std::string bad = lagb::checks_preconditions(opt->mesh, P.dim, opt->rs, opt->ok, opt->ot, opt->ode_solver_type,
+                                                            opt->t_final, opt->cfl);
+         if (!bad.empty()) { lagb::set_error(bad); rc = LAGB_ERR_INVALID; last_step = true; }
+      }
       for (; !last_step; ti++)
       {
          if (t + dt >= opt->t_final) { dt = opt->t_final - t; last_step = true; }
@@ -461,12 +471,24 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
             if (dt_est > 1.25*dt) { dt *= 1.02; }
             if (opt->e2e_host_state) { LAGHOS_CHECK(lagb_memcpy_d2h_bg(ctx, S_pin, S.Read(), N)); }   // overlaps the next step's start
             const bool print = opt->verbose && (last_step || (ti % std::max(1, opt->vis_steps)) == 0);
-            if (hist_cap > 0 || print || last_step)
+            if (hist_cap > 0 || print || last_step || opt->check)
             {
                const double nrm = e_norm();
                res->e_norm = nrm; res->ti_last = ti;
                if (hist && n_hist < hist_cap) { hist[2*n_hist] = ti; hist[2*n_hist + 1] = nrm; n_hist++; }
                if (print && opt->rank == 0) { printf("step %5d,\tt = %5.4f,\tdt = %5.6f,\t|e| = %.10e\n", ti, t, dt, nrm); }
+               if (opt->check)
+               {
+                  std::string msg;
+                  if (lagb::checks_step(P.dim, opt->problem, ti, nrm, opt->check_eps > 0 ? opt->check_eps : 1e-13, checks, msg) < 0)
+                  {
+                     // the reference aborts here (MFEM_VERIFY); a library call reports the failure instead: the loop
+                     // stops, the context is released below and the status + message go back to the caller
+                     if (opt->rank == 0) { printf("%.15e\n", nrm); }
+                     lagb::set_error("check failed: " + msg);
+                     rc = LAGB_ERR_INVALID; last_step = true;
+                  }
+               }
             }
             if ((opt->gfprint || opt->visit) && (last_step || (ti % std::max(1, opt->vis_steps)) == 0))
             {
@@ -500,6 +522,8 @@ extern "C" int lagb_laghos_run(const lagb_run_options *opt, lagb_run_result *res
       LAGHOS_CHECK(lagb_profile_mass_get(ctx, &res->mass_kernel_seconds, &res->mass_kernel_launches));
       res->mass_kernel_ncomp = opt->batched_pcg ? P.dim : 1;
       res->steps = steps; res->t = t; res->dt = dt; res->stages = stages; res->n_hist = n_hist;
+      res->checks = checks;
+      if (opt->check && rc == 0 && checks != 2) { lagb::set_error("Check error!"); rc = LAGB_ERR_INVALID; }   // laghos.cpp:926
       res->wall_seconds = wall;
       res->kernel_launches = lagb_kernel_launch_count() - launches0;
       res->h2d_bytes_per_step = opt->e2e_host_state ? (int64_t)N*8 : 0;

@@ -268,6 +268,8 @@ typedef struct lagb_run_options
    const char *basename;    // -k, default "results/Laghos" (the directory must exist)
    int check_exact_sedov;   // -err: problem 1: L2 error of the density against the exact Sedov solution at t_final (laghos.cpp:1009-1085)
    int v_error;             // 1: problems 0 / 4: L_inf, L_1, L_2 velocity errors at the end of the run (laghos.cpp:970-982; host)
+   int check;               // --checks (laghos.cpp:904-926): |e| against the reference's table after every accepted step, two hits required
+   double check_eps;        // relative tolerance of the check; <= 0: the reference's 1e-13
 } lagb_run_options;
 
 typedef struct lagb_run_result
@@ -289,6 +291,7 @@ typedef struct lagb_run_result
    double energy_init, energy_final; // IE + KE before / after the run (laghos.cpp:664-665, 956-962 "Energy diff")
    double v_err[3];                 // v_error: L_inf, L_1, L_2 of v - v0(x) (problems 0 and 4), else 0
    double density_l2_err;           // check_exact_sedov: "Density L2 error", else 0
+   int checks;                      // check: number of table entries that fired (2 for a complete run)
 } lagb_run_result;
 
 // hist: [2*hist_cap] (ti, |e|) pairs after every accepted step; S_out (optional): final state on the host

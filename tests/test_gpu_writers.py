@@ -69,3 +69,16 @@ def test_sedov_density_error_of_a_run(built):
     # a coarse mesh smears the shock: the error is O(1) times sqrt(shock volume), far below the ambient norm 1
     assert 0.01 < r["density_l2_err"] < 1.0
     assert run(**cfg, t_final=0.01)["density_l2_err"] == 0.0
+
+
+def test_checks_mode_of_a_run(built):
+    """--checks (laghos.cpp:904-926): the driver loop compares |e| with the reference's table itself.  The B200 path
+    sums in a different order than the reference (atomics, batched PCG): gate 1e-11 as in test_gpu_end_to_end.py."""
+    from laghos_b200.api import LagbError, run
+    kw = dict(rs=0, ok=2, ot=1, t_final=0.6, cfl=0.5, cg_tol=1e-14, check=True, check_eps=1e-11)
+    assert run(mesh="square01_quad", problem=1, **kw)["checks"] == 2
+    assert run(mesh="cube01_hex", problem=1, **kw)["checks"] == 2
+    with pytest.raises(LagbError, match="check: rs, rp"):
+        run(mesh="square01_quad", problem=1, **dict(kw, rs=1))
+    with pytest.raises(LagbError, match="check failed: P1, #5"):      # a loose CG moves |e| by far more than 1e-11
+        run(mesh="square01_quad", problem=1, **dict(kw, cg_tol=1e-4))
